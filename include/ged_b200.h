@@ -1,0 +1,137 @@
+/*
+ * ged_b200.h -- C-ABI of the B200-native GED lower-level solver (libged_b200.so).
+ *
+ * The reference (Thinklab-SJTU/PPO-BiHyb) has no FFI for this path: the "operator interface" is a set of plain
+ * Python functions in utils/ged_env.py.  Each entry point below names the reference function(s) it replaces; the
+ * Python host code in ppo-bihyb_b200/ged_env.py keeps the reference's names and signatures on top of these.
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer inside the descriptors is a DEVICE pointer unless the field says "host";
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*), never synchronise, never allocate;
+ *   - return value: 0 on success, a GED_E_* code otherwise; ged_last_error() gives the message (thread local);
+ *   - per-solve failures (invalid cost entries, malformed graphs) are reported in `status[b]`, not by the call;
+ *   - a "pair" is (graph 1, graph 2); R = n1+1, C = n2+1 (one dummy node each, utils/ged_env.py:188-201);
+ *     an R x C matrix of a pair is stored dense row-major with row stride C (its own C, not the batch maximum).
+ */
+#ifndef GED_B200_H
+#define GED_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GED_ABI_VERSION 1
+
+/* call-level errors */
+#define GED_OK 0
+#define GED_E_BADARG 1       /* null pointer / negative size / inconsistent descriptor            */
+#define GED_E_TOO_LARGE 2    /* pair does not fit the shared-memory size classes (see ged_limits) */
+#define GED_E_CUDA 3         /* a CUDA runtime call failed (message has the CUDA error string)    */
+
+/* per-solve status bits written to status[b] */
+#define GED_ST_OK 0
+#define GED_ST_INVALID_COST 1   /* NaN or -inf reached the LAP (scipy raises ValueError, ged_env.py:407)   */
+#define GED_ST_INFEASIBLE 2     /* LAP infeasible (all +inf)                                              */
+#define GED_ST_BAD_GRAPH 4      /* adjacency not symmetric 0/1 off the diagonal                           */
+
+#define GED_SOLVER_IPFP 0       /* ipfp_ged       utils/ged_env.py:256-289 */
+#define GED_SOLVER_HUNGARIAN 1  /* hungarian_ged  utils/ged_env.py:303-305 */
+
+/* A set of base pairs in factor form (what construct_k, utils/ged_env.py:160-228, would expand into K).
+ * Graph g's adjacency is n x n uint8, row-major, at adj + adj_off[g]; only "non-zero off the diagonal" matters
+ * (the mask of ged_env.py:205-211 removes the diagonal).  Labels select the AIDS node metric of
+ * ged_env.py:230-234 (substitution 0/1, insertion/deletion 1, dummy-dummy 0); if node_cost != NULL it is used
+ * instead: pair p's R x C fp32 matrix (diag(K) reshaped) at node_cost + node_cost_off[p]. */
+typedef struct ged_pairs {
+    int32_t num_pairs;
+    const int32_t *n1, *n2;                   /* [num_pairs] */
+    const uint8_t *adj1; const int64_t *adj1_off;
+    const uint8_t *adj2; const int64_t *adj2_off;
+    const int32_t *lab1; const int64_t *lab1_off;   /* may be NULL when node_cost is given */
+    const int32_t *lab2; const int64_t *lab2_off;
+    const float *node_cost; const int64_t *node_cost_off;  /* optional */
+    int32_t max_n1, max_n2;                   /* host-known upper bounds over the set (sizes shared memory) */
+} ged_pairs;
+
+/* One batch of B candidate solves.  Candidate b works on base pair base_idx[b] (identity if NULL, then
+ * B == num_pairs) with the undirected edge (edit_u[b], edit_v[b]) of graph 1 toggled first, exactly as
+ * GEDenv.step does (utils/ged_env.py:110-121); edit_u == NULL or a negative entry means "no edit".
+ * The solve runs on the edited pair; `ged` is scored on the UNEDITED base pair (ged_env.py:122,158). */
+typedef struct ged_solve_desc {
+    ged_pairs pairs;
+    int32_t B;
+    const int32_t *base_idx;
+    const int32_t *edit_u, *edit_v;
+    int32_t max_iter;        /* ipfp_ged's max_iter (100 in the reference) */
+    int32_t solver_kind;     /* GED_SOLVER_* */
+    /* Optional teacher forcing: start IPFP from x_init instead of the Hungarian initialiser.  Candidate b's R x C
+     * matrix is at x_init + b * mat_stride. */
+    const float *x_init;
+    int64_t mat_stride;      /* elements between consecutive candidates in x_init / x_out / workspace / trace;
+                                must be >= (max_n1+1)*(max_n2+1) */
+    float *workspace;        /* B * mat_stride floats of scratch (the fractional iterate lives here, L2 resident) */
+} ged_solve_desc;
+
+typedef struct ged_solve_out {
+    float *ged;              /* [B]  x^T K_base x of the returned solution  (GEDenv.comp_ged, ged_env.py:245-253) */
+    float *ged_edited;       /* [B]  optional: same on the edited pair's K                                       */
+    int32_t *rowmatch;       /* [B * match_stride_1]  column of row i, n2 = deleted                               */
+    int32_t *colmatch;       /* [B * match_stride_2]  row of column a, n1 = inserted                              */
+    int32_t match_stride_1, match_stride_2;   /* >= max_n1 / max_n2 */
+    int32_t *iters;          /* [B]  IPFP iterations executed                                                     */
+    int32_t *status;         /* [B]  GED_ST_* bits                                                                */
+    float *x_out;            /* optional dense 0/1 solution, R x C at x_out + b * mat_stride                       */
+    /* Optional per-iteration trace (tests / diagnostics); any pointer may be NULL.  T = max_iter. */
+    float *tr_cost;          /* [B][T][mat_stride]  cost = K v at iteration start                                 */
+    float *tr_x_after;       /* [B][T][mat_stride]  v after the line-search update                                */
+    double *tr_scalars;      /* [B][T][6]  s_vv, s_vb, ub, alpha, beta, t0                                        */
+    int32_t *tr_rowmatch;    /* [B][T][match_stride_1]  LAP projection b of each iteration                        */
+    int32_t *tr_colmatch;    /* [B][T][match_stride_2]                                                            */
+    float *tr_init_cost;     /* [B][mat_stride]  node_cost_mat of heuristic_prediction_hun (ged_env.py:315)        */
+    int32_t *tr_init_rowmatch, *tr_init_colmatch;   /* [B][match_stride_*] Hungarian initialiser                  */
+    unsigned long long *tr_lap_steps;               /* [B] LAP scan steps executed (row visits)                    */
+} ged_solve_out;
+
+/* Replaces GEDenv.step / solve_feasible_ged / ipfp_ged / hungarian_ged for a whole candidate batch
+ * (utils/ged_env.py:110-158, 256-289, 303-326).  One warp per candidate, pair state in shared memory. */
+int ged_solve_batch(const ged_solve_desc *desc, const ged_solve_out *out, void *stream);
+
+/* Replaces hungarian_lap (utils/ged_env.py:329-351) incl. scipy's linear_sum_assignment with its exact traversal
+ * and tie-break order.  cost: B matrices, (n1[b]+1) x (n2[b]+1) fp32 at cost + b * mat_stride.
+ * lb[b] = sum(pred_x * cost) (fp64 accumulate, rounded to fp32). */
+int ged_lsape_batch(int32_t B, const int32_t *n1, const int32_t *n2, int32_t max_n1, int32_t max_n2,
+                    const float *cost, int64_t mat_stride,
+                    int32_t *rowmatch, int32_t match_stride_1, int32_t *colmatch, int32_t match_stride_2,
+                    float *lb, int32_t *status, void *stream);
+
+/* Replaces torch.mm(k, v) of ipfp_ged (utils/ged_env.py:269) without K: cost_b = K_b vec(X_b) from the factors. */
+int ged_kv_batch(const ged_pairs *pairs, const float *x, float *cost, int64_t mat_stride, void *stream);
+
+/* Replaces GEDenv.comp_ged (utils/ged_env.py:245-253) for binary x given as assignments: the coalesced edit-cost
+ * reduction.  Candidate b scores (rowmatch_b, colmatch_b) on base pair base_idx[b] (identity if NULL). */
+int ged_score_batch(const ged_pairs *pairs, int32_t B, const int32_t *base_idx,
+                    const int32_t *rowmatch, int32_t match_stride_1, const int32_t *colmatch, int32_t match_stride_2,
+                    float *ged, void *stream);
+
+/* comp_ged against a DENSE K (any x, any K): out[b] = x_b^T K_b x_b, K_b is nk x nk fp32 at k + b*k_stride
+ * (k_stride == 0 shares one K), x_b has nk entries at x + b*nk.  HBM-bound float4 streaming reduction. */
+int ged_quadform_dense_batch(int32_t B, int32_t nk, const float *k, int64_t k_stride, const float *x, float *out,
+                             void *stream);
+
+/* Size limits of this build: largest n1+n2 and largest (n1+1)*(n2+1) a single warp's shared-memory slice holds. */
+void ged_limits(int32_t *max_nodes_per_graph, int32_t *max_matrix_elems);
+
+/* Bytes of dynamic shared memory one solve uses for the given bounds (diagnostics / occupancy planning). */
+int64_t ged_solve_smem_bytes(int32_t max_n1, int32_t max_n2);
+
+int ged_abi_version(void);
+const char *ged_version(void);
+const char *ged_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GED_B200_H */
