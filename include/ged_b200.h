@@ -65,6 +65,11 @@ typedef struct ged_solve_desc {
     int32_t B;
     const int32_t *base_idx;
     const int32_t *edit_u, *edit_v;
+    /* Optional scoring graph: GEDenv.step scores on `ori_k`, the K of the ORIGINAL pair, while graph 1 may already
+     * carry earlier edits (utils/ged_env.py:122; ged_ppo_bihyb_train.py:286-298).  If score_adj1 != NULL candidate b is
+     * scored with graph 1 := the n1 x n1 uint8 adjacency at score_adj1 + score_adj1_off[score_idx[b]] (same n1,
+     * same labels, same graph 2); otherwise with the base pair's own unedited graph 1. */
+    const uint8_t *score_adj1; const int64_t *score_adj1_off; const int32_t *score_idx;
     int32_t max_iter;        /* ipfp_ged's max_iter (100 in the reference) */
     int32_t solver_kind;     /* GED_SOLVER_* */
     /* Optional teacher forcing: start IPFP from x_init instead of the Hungarian initialiser.  Candidate b's R x C
@@ -116,10 +121,13 @@ int ged_score_batch(const ged_pairs *pairs, int32_t B, const int32_t *base_idx,
                     const int32_t *rowmatch, int32_t match_stride_1, const int32_t *colmatch, int32_t match_stride_2,
                     float *ged, void *stream);
 
-/* comp_ged against a DENSE K (any x, any K): out[b] = x_b^T K_b x_b, K_b is nk x nk fp32 at k + b*k_stride
- * (k_stride == 0 shares one K), x_b has nk entries at x + b*nk.  HBM-bound float4 streaming reduction. */
+/* comp_ged against a DENSE K (any x, any K; utils/ged_env.py:245-253): out[b] = x_b^T K_b x_b.  K_b is nk x nk fp32
+ * at k + b*k_stride (k_stride == 0 shares one K), x_b has nk entries at x + b*nk.  HBM-bound float4 streaming
+ * reduction; rows of K whose x entry is zero are skipped (binary x touches n1+n2 rows only).  partial_ws needs
+ * ged_quadform_ws_elems(B, nk) floats. */
+int64_t ged_quadform_ws_elems(int32_t B, int32_t nk);
 int ged_quadform_dense_batch(int32_t B, int32_t nk, const float *k, int64_t k_stride, const float *x, float *out,
-                             void *stream);
+                             float *partial_ws, void *stream);
 
 /* Size limits of this build: largest n1+n2 and largest (n1+1)*(n2+1) a single warp's shared-memory slice holds. */
 void ged_limits(int32_t *max_nodes_per_graph, int32_t *max_matrix_elems);

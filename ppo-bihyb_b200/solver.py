@@ -1,0 +1,201 @@
+"""Batched entry points over the C-ABI (``include/ged_b200.h``).  Device tensors in, device tensors out, launches on
+torch's current stream, no synchronisation unless ``check=True`` asks for the per-solve status."""
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .graphs import PairSet
+
+SOLVERS = {"ipfp": _lib.GED_SOLVER_IPFP, "hungarian": _lib.GED_SOLVER_HUNGARIAN}
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+@dataclass
+class SolveResult:
+    ged: torch.Tensor                 # [B] fp32, objective on the base (unedited) pair
+    ged_edited: torch.Tensor          # [B] fp32, objective on the edited pair
+    rowmatch: torch.Tensor            # [B, max_n1] int32 (column of row i; n2 = deleted)
+    colmatch: torch.Tensor            # [B, max_n2] int32 (row of column a; n1 = inserted)
+    iters: torch.Tensor               # [B] int32
+    status: torch.Tensor              # [B] int32
+    x: Optional[torch.Tensor] = None  # [B, mat_stride] dense 0/1 solutions (R x C with the pair's own C)
+    trace: dict = field(default_factory=dict)
+
+    def raise_on_error(self):
+        st = self.status
+        if bool((st != 0).any().item()):
+            bad = int(torch.nonzero(st)[0].item())
+            code = int(st[bad].item())
+            if code & _lib.GED_ST_BAD_GRAPH:
+                raise ValueError(f"solve {bad}: adjacency must be symmetric 0/1 off the diagonal (no multi-edges)")
+            if code & _lib.GED_ST_INVALID_COST:
+                raise ValueError(f"solve {bad}: matrix contains invalid numeric entries")   # scipy's message
+            raise ValueError(f"solve {bad}: cost matrix is infeasible")
+        return self
+
+
+def _as_i32(t, device):
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(t, np.int32))
+    return t.to(device=device, dtype=torch.int32, non_blocking=True).contiguous()
+
+
+def solve_batch(pairs: PairSet, base_idx=None, edit_u=None, edit_v=None, solver: str = "ipfp", max_iter: int = 100,
+                x_init: Optional[torch.Tensor] = None, dense_x: bool = False, trace: bool = False,
+                check: bool = False, score_adj1: Optional[torch.Tensor] = None,
+                score_adj1_off: Optional[torch.Tensor] = None, score_idx=None) -> SolveResult:
+    """All candidate solves of one batch in one launch (``ged_solve_batch``).
+
+    Candidate b = base pair ``base_idx[b]`` with edge ``(edit_u[b], edit_v[b])`` of graph 1 toggled
+    (reference ``GEDenv.step``, ``utils/ged_env.py:110-124``)."""
+    lib = _lib.require_cuda()
+    if solver not in SOLVERS:
+        raise NotImplementedError(f"{solver} is not implemented.")      # reference ged_env.py:156
+    dev = pairs.device
+    base_idx = _as_i32(base_idx, dev)
+    edit_u, edit_v = _as_i32(edit_u, dev), _as_i32(edit_v, dev)
+    B = pairs.num_pairs if base_idx is None else int(base_idx.numel())
+    score_idx = _as_i32(score_idx, dev)
+    ms, m1, m2 = pairs.mat_stride, pairs.max_n1, pairs.max_n2
+    i32 = dict(device=dev, dtype=torch.int32)
+    f32 = dict(device=dev, dtype=torch.float32)
+    res = SolveResult(ged=torch.empty(B, **f32), ged_edited=torch.empty(B, **f32),
+                      rowmatch=torch.empty(B, m1, **i32), colmatch=torch.empty(B, m2, **i32),
+                      iters=torch.empty(B, **i32), status=torch.empty(B, **i32))
+    workspace = torch.empty(B * ms, **f32) if solver == "ipfp" else None
+    if x_init is not None:
+        x_init = x_init.to(**f32).contiguous()
+        assert x_init.numel() == B * ms, "x_init must be [B, mat_stride]"
+    if dense_x:
+        res.x = torch.zeros(B, ms, **f32)
+    T = max_iter
+    tr = res.trace
+    if trace:
+        tr.update(cost=torch.zeros(B, T, ms, **f32), x_after=torch.zeros(B, T, ms, **f32),
+                  scalars=torch.zeros(B, T, 6, device=dev, dtype=torch.float64),
+                  rowmatch=torch.zeros(B, T, m1, **i32), colmatch=torch.zeros(B, T, m2, **i32),
+                  init_cost=torch.zeros(B, ms, **f32), init_rowmatch=torch.zeros(B, m1, **i32),
+                  init_colmatch=torch.zeros(B, m2, **i32), lap_steps=torch.zeros(B, device=dev, dtype=torch.int64))
+    p = _lib.ptr
+    desc = _lib.GedSolveDesc(pairs.c_struct(), B, p(base_idx, _lib.c_i32p), p(edit_u, _lib.c_i32p), p(edit_v, _lib.c_i32p),
+                             p(score_adj1, _lib.c_u8p), p(score_adj1_off, _lib.c_i64p), p(score_idx, _lib.c_i32p),
+                             int(max_iter), SOLVERS[solver], p(x_init, _lib.c_f32p), ms, p(workspace, _lib.c_f32p))
+    out = _lib.GedSolveOut(p(res.ged, _lib.c_f32p), p(res.ged_edited, _lib.c_f32p), p(res.rowmatch, _lib.c_i32p),
+                           p(res.colmatch, _lib.c_i32p), m1, m2, p(res.iters, _lib.c_i32p), p(res.status, _lib.c_i32p),
+                           p(res.x, _lib.c_f32p),
+                           p(tr.get("cost"), _lib.c_f32p), p(tr.get("x_after"), _lib.c_f32p), p(tr.get("scalars"), _lib.c_f64p),
+                           p(tr.get("rowmatch"), _lib.c_i32p), p(tr.get("colmatch"), _lib.c_i32p),
+                           p(tr.get("init_cost"), _lib.c_f32p), p(tr.get("init_rowmatch"), _lib.c_i32p),
+                           p(tr.get("init_colmatch"), _lib.c_i32p), p(tr.get("lap_steps"), _lib.c_u64p))
+    with torch.cuda.device(dev):
+        _lib.check(lib.ged_solve_batch(desc, out, _stream(dev)), "ged_solve_batch")
+    if workspace is not None:
+        workspace.record_stream(torch.cuda.current_stream(dev))
+    if check:
+        res.raise_on_error()
+    return res
+
+
+def lsape_batch(cost: torch.Tensor, n1, n2, check: bool = False):
+    """``hungarian_lap`` (reference ``utils/ged_env.py:329-351``) for B cost matrices.
+
+    ``cost`` is [B, mat_stride] with matrix b stored R_b x C_b row-major at the start of its row, or [B, R, C] when all
+    pairs share one size.  Returns (rowmatch [B,max_n1], colmatch [B,max_n2], lb [B], status [B])."""
+    lib = _lib.require_cuda()
+    dev = cost.device
+    n1h = np.atleast_1d(np.asarray(n1, np.int32))
+    n2h = np.atleast_1d(np.asarray(n2, np.int32))
+    B = cost.shape[0]
+    if n1h.size == 1 and B > 1:
+        n1h, n2h = np.repeat(n1h, B), np.repeat(n2h, B)
+    m1, m2 = max(int(n1h.max()), 1), max(int(n2h.max()), 1)
+    cost = cost.to(torch.float32).reshape(B, -1).contiguous()
+    ms = cost.shape[1]
+    n1d, n2d = _as_i32(n1h, dev), _as_i32(n2h, dev)
+    rm = torch.empty(B, m1, device=dev, dtype=torch.int32)
+    cm = torch.empty(B, m2, device=dev, dtype=torch.int32)
+    lb = torch.empty(B, device=dev, dtype=torch.float32)
+    st = torch.empty(B, device=dev, dtype=torch.int32)
+    p = _lib.ptr
+    with torch.cuda.device(dev):
+        _lib.check(lib.ged_lsape_batch(B, p(n1d, _lib.c_i32p), p(n2d, _lib.c_i32p), m1, m2, p(cost, _lib.c_f32p), ms,
+                                       p(rm, _lib.c_i32p), m1, p(cm, _lib.c_i32p), m2, p(lb, _lib.c_f32p),
+                                       p(st, _lib.c_i32p), _stream(dev)), "ged_lsape_batch")
+    if check and bool((st != 0).any().item()):
+        code = int(st[torch.nonzero(st)[0]].item())
+        raise ValueError("matrix contains invalid numeric entries" if code & _lib.GED_ST_INVALID_COST
+                         else "cost matrix is infeasible")
+    return rm, cm, lb, st
+
+
+def kv_batch(pairs: PairSet, x: torch.Tensor) -> torch.Tensor:
+    """cost_b = K_b vec(X_b) without K (replaces ``torch.mm(k, v)``, reference ``utils/ged_env.py:269``).
+    ``x`` and the result are [P, mat_stride]."""
+    lib = _lib.require_cuda()
+    dev = pairs.device
+    x = x.to(device=dev, dtype=torch.float32).reshape(pairs.num_pairs, -1).contiguous()
+    ms = x.shape[1]
+    out = torch.zeros_like(x)
+    p = _lib.ptr
+    cs = pairs.c_struct()
+    with torch.cuda.device(dev):
+        _lib.check(lib.ged_kv_batch(cs, p(x, _lib.c_f32p), p(out, _lib.c_f32p), ms, _stream(dev)), "ged_kv_batch")
+    return out
+
+
+def score_batch(pairs: PairSet, rowmatch: torch.Tensor, colmatch: torch.Tensor, base_idx=None) -> torch.Tensor:
+    """``comp_ged`` of binary solutions given as assignments (reference ``utils/ged_env.py:245-253``)."""
+    lib = _lib.require_cuda()
+    dev = pairs.device
+    rowmatch = rowmatch.to(device=dev, dtype=torch.int32).contiguous()
+    colmatch = colmatch.to(device=dev, dtype=torch.int32).contiguous()
+    base_idx = _as_i32(base_idx, dev)
+    B = rowmatch.shape[0]
+    out = torch.empty(B, device=dev, dtype=torch.float32)
+    p = _lib.ptr
+    cs = pairs.c_struct()
+    with torch.cuda.device(dev):
+        _lib.check(lib.ged_score_batch(cs, B, p(base_idx, _lib.c_i32p), p(rowmatch, _lib.c_i32p), rowmatch.shape[1],
+                                       p(colmatch, _lib.c_i32p), colmatch.shape[1], p(out, _lib.c_f32p), _stream(dev)),
+                   "ged_score_batch")
+    return out
+
+
+def quadform_dense(k: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """x^T K x against a dense K (``comp_ged`` on a materialised K).  k: [nk,nk] or [B,nk,nk]; x: [B,nk] or [nk]."""
+    lib = _lib.require_cuda()
+    dev = k.device
+    k = k.to(torch.float32).contiguous()
+    shared = k.dim() == 2
+    nk = k.shape[-1]
+    x = x.to(device=dev, dtype=torch.float32).reshape(-1, nk).contiguous()
+    B = x.shape[0]
+    if not shared:
+        assert k.shape[0] == B
+    out = torch.empty(B, device=dev, dtype=torch.float32)
+    ws = torch.empty(max(1, lib.ged_quadform_ws_elems(B, nk)), device=dev, dtype=torch.float32)
+    p = _lib.ptr
+    with torch.cuda.device(dev):
+        _lib.check(lib.ged_quadform_dense_batch(B, nk, p(k, _lib.c_f32p), 0 if shared else nk * nk, p(x, _lib.c_f32p),
+                                                p(out, _lib.c_f32p), p(ws, _lib.c_f32p), _stream(dev)),
+                   "ged_quadform_dense_batch")
+    ws.record_stream(torch.cuda.current_stream(dev))
+    return out
+
+
+def match_to_dense(rowmatch: torch.Tensor, colmatch: torch.Tensor, n1: int, n2: int) -> torch.Tensor:
+    """(rowmatch[:n1], colmatch[:n2]) -> the (n1+1) x (n2+1) 0/1 matrix ``hungarian_lap`` returns (``ged_env.py:344-347``)."""
+    x = torch.zeros(n1 + 1, n2 + 1, device=rowmatch.device, dtype=torch.float32)
+    if n1:
+        x[torch.arange(n1, device=x.device), rowmatch[:n1].long()] = 1
+    if n2:
+        x[n1, :n2] = (colmatch[:n2] == n1).to(torch.float32)
+    return x
