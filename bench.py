@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""Throughput of the GED lower-level solver hot path: IPFP pair-solves/sec at AIDS-50+ shape (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" = one pass of the hot path over one candidate batch: every candidate (base pair, edge edit) of the batch is
+solved by IPFP (Hungarian start, <=100 Frank-Wolfe iterations with a SciPy-order LSAPE projection each) and scored on
+its base pair -- what GEDenv.step does per candidate (reference utils/ged_env.py:110-158), for a whole beam-search /
+rollout fan-out at once.  Workload = BASELINE.json configs[2]: synthetic AIDS-50+-shaped pairs (n = 50..100, mean ~60),
+`--pairs` base pairs x `--edits` uniform random edge toggles per GPU (weak scaling: every rank owns its own shard of
+the candidate list; no data-path collective, the B x 4-byte objectives are all-gathered at the end of each step).
+
+Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` goes through the host-buffer
+entry point (pinned host -> device copies, solve, objectives back to the host) inside the timed region.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ipfp_ged_pair_solves_per_sec"
+UNIT = "pair-solves/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="aids-50+")
+    ap.add_argument("--pairs", type=int, default=64, help="base pairs per GPU")
+    ap.add_argument("--edits", type=int, default=128, help="candidate edge edits per base pair")
+    ap.add_argument("--max-iter", type=int, default=100)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="candidates in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args, rank):
+    from ppo_bihyb_b200 import synthetic
+    pairs = synthetic.make_pairs(args.config, args.pairs, seed_offset=100 + rank)
+    base, eu, ev = synthetic.make_edits(pairs, args.edits, seed_offset=100 + rank)
+    return pairs, base, eu, ev
+
+
+def workload_name(args, world):
+    return (f"{args.config} synthetic pairs, {args.pairs} base pairs x {args.edits} edge-edit candidates per GPU "
+            f"({args.pairs * args.edits * world} candidate solves per step), max_iter {args.max_iter}")
+
+
+# ---- CPU baseline: the oracle port on the box's host cores ----------------------------------------------------------
+def cpu_baseline(args, sample, threads):
+    """Times oracle/ged_oracle.c (the C restatement of the reference's path; `kind: port`) on a bounded sample of the
+    same workload, `threads` solves in flight (ctypes releases the GIL).  The reference itself is Python/torch/SciPy and
+    cannot travel to this box; its measured 1-thread times are recorded in BASELINE.md / DESIGN.md."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import ged_oracle as go
+    from ppo_bihyb_b200.graphs import label_node_cost
+    pairs, base, eu, ev = workload(args, 0)
+    go.lib()
+    idx = [int(i) for i in (len(base) * (2 * t + 1) // (2 * sample) for t in range(sample))]   # spread over the batch
+
+    def one(b):
+        g1, g2 = pairs[base[b]]
+        return go.solve(g1.adj, g2.adj, label_node_cost(g1.labels, g2.labels), edit=(int(eu[b]), int(ev[b])),
+                        max_iter=args.max_iter)["ged"]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        geds = list(ex.map(one, idx))
+    dt = time.perf_counter() - t0
+    return len(idx) / dt, dt, idx, geds
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path (oracle port, all host threads)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = args.cpu_sample or max(threads, min(256, 4 * threads))
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(args, max(threads, 8), threads)
+    vals, dts = [], []
+    for _ in range(max(args.steps, 1)):
+        v, dt, _, _ = cpu_baseline(args, sample, threads)
+        vals.append(v)
+        dts.append(dt)
+    value = sample * len(vals) / sum(dts)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(dts) / len(dts), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args, 1), "sample": f"{sample} candidates per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} candidates of the workload spread evenly over the batch, {threads} threads, "
+                                   "oracle/ged_oracle.c (C restatement of utils/ged_env.py IPFP/LSAPE path)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- clocks ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        pw = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(rows), "power_w_max": max(pw) if pw else None}
+
+
+def algorithmic_bytes(pairs, base):
+    """Compulsory HBM traffic of a step: per candidate the two uint8 adjacencies, the labels,
+    the 12-byte (base, u, v) record in; the assignment (4(n1+n2)) and 16 bytes of objective/iters/status out."""
+    tot = 0
+    for b in base:
+        n1, n2 = pairs[b][0].n, pairs[b][1].n
+        tot += n1 * n1 + n2 * n2 + 4 * (n1 + n2) + 12 + 4 * (n1 + n2) + 16
+    return tot
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:       # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from ppo_bihyb_b200 import _lib, sharding, solver
+    from ppo_bihyb_b200.graphs import PairSet
+
+    _lib.require_cuda()                    # fails loudly when the CUDA library or the GPU is missing: no fallback
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    pairs, base, eu, ev = workload(args, rank)
+    B = len(base)
+    ps = PairSet.from_host(pairs, dev)
+    base_d = torch.from_numpy(base).to(dev)
+    eu_d, ev_d = torch.from_numpy(eu).to(dev), torch.from_numpy(ev).to(dev)
+    plan = solver.make_plan(ps, base)
+    host_batch = solver.HostBatch(pairs, base, eu, ev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    local_idx = np.arange(B, dtype=np.int64) + rank * B                  # this rank's slice of the global candidate list
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_device():
+        res = solver.solve_batch(ps, base_idx=base_d, edit_u=eu_d, edit_v=ev_d, max_iter=args.max_iter, plan=plan)
+        if world > 1:                      # reward gather: the only collective of the path (B x 4 bytes per rank)
+            allged = torch.empty(world * B, dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(allged, res.ged)
+        return res
+
+    def timed(fn, steps):
+        """K steps, each bracketed by CUDA events on the launching stream, L2 flushed before each; returns ms list."""
+        out = []
+        for _ in range(steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn()
+            e1.record()
+            e1.synchronize()
+            out.append((e0.elapsed_time(e1), r))
+        return out
+
+    # ---- device-resident timing (`value`) -----------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t0 = time.perf_counter()
+    runs = timed(step_device, args.steps)
+    barrier()
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    ms_total = sum(ms for ms, _ in runs)
+    res = runs[-1][1]
+    launches = sum(r.launches for _, r in runs)
+    status_bad = int((res.status != 0).sum().item())
+    mean_iters = float(res.iters.float().mean().item())
+    mean_ged = float(res.ged.mean().item())
+
+    # ---- end-to-end timing through the host-buffer entry point (`e2e`) ---------------------------------------------------
+    for _ in range(2):
+        solver.solve_batch_host(host_batch, dev, max_iter=args.max_iter)
+    barrier()
+    e2e_ms = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ged_host = solver.solve_batch_host(host_batch, dev, max_iter=args.max_iter)     # H2D + solve + D2H + sync
+        e1.record()
+        e1.synchronize()
+        e2e_ms.append(e0.elapsed_time(e1))
+    barrier()
+    assert np.array_equal(ged_host.numpy(), res.ged.cpu().numpy()), "host-buffer path and device path disagree"
+
+    tmax = torch.tensor([ms_total, sum(e2e_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total, e2e_total = float(tmax[0]), float(tmax[1])
+    total_candidates = B * world
+
+    if rank == 0:
+        value = total_candidates * args.steps / (ms_total * 1e-3)
+        e2e_value = total_candidates * args.steps / (e2e_total * 1e-3)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak, which = (peaks["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+        alg = algorithmic_bytes(pairs, base)
+        kernel_ms = ms_total / args.steps             # the solve launches ARE the step (one kernel, one launch per size class)
+        achieved = alg / (kernel_ms * 1e-3) / 1e9
+        extra = {}
+        try:
+            extra = json.load(open(os.path.join(ROOT, "profiles", "roofline_r01.json")))
+        except OSError:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args, world), "l2": "flushed between steps (256 MiB write)",
+                       "mean_ipfp_iterations": mean_iters, "mean_ged": mean_ged, "failed_solves": status_bad,
+                       "parity": "bit-exact vs canonical-order oracle (tests/, smoke)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host_batch.h2d_bytes,
+                    "d2h_bytes_per_step": host_batch.d2h_bytes, "ms_per_step": e2e_total / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": extra.get("dram_bytes_per_launch"), "peak_source": which,
+                         "algorithmic_bytes_per_step": alg, "kernel": "ged_solve_kernel",
+                         "note": "compute per byte is ~1e3 instructions: the kernel is bound by instruction issue and "
+                                 "shared-memory latency of the sequential LAP scan, not by HBM (DESIGN.md); the issue-slot "
+                                 "fraction from ncu is in `issue_active_pct`",
+                         "issue_active_pct": extra.get("issue_active_pct")},
+        }
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            sample = args.cpu_sample or max(threads, min(128, 2 * threads))
+            v, dt, idx, geds = cpu_baseline(args, sample, threads)
+            same = bool(np.array_equal(np.asarray(geds, np.float32), res.ged.cpu().numpy()[idx]))
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{sample} candidates of the same workload spread evenly over rank 0's batch, "
+                                              f"{dt:.1f} s, oracle/ged_oracle.c on {threads} threads",
+                                    "gpu_results_identical_on_sample": same}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

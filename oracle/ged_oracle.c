@@ -50,6 +50,14 @@
  * Traversal order, tie-break and dual-update association follow scipy exactly.
  * col4row[nr] out, row4col[nc] out.  *steps (optional) counts inner scan steps (rows visited).
  * ---------------------------------------------------------------------------------------------------------- */
+/* diagnostics for kernel design (how often SciPy's tie-break rule actually decides a step) */
+static int64_t g_stat_steps = 0, g_stat_tie_steps = 0, g_stat_tie_unassigned = 0;
+void ged_oracle_lsap_stats(int64_t *out, int reset)
+{
+    out[0] = g_stat_steps; out[1] = g_stat_tie_steps; out[2] = g_stat_tie_unassigned;
+    if (reset) g_stat_steps = g_stat_tie_steps = g_stat_tie_unassigned = 0;
+}
+
 int ged_oracle_lsap(int nr, int nc, const double *cost, int32_t *col4row, int32_t *row4col, int64_t *steps)
 {
     if (nr > nc) return GED_ERR_INVALID;
@@ -91,6 +99,13 @@ int ged_oracle_lsap(int nr, int nc, const double *cost, int32_t *col4row, int32_
             }
             minVal = lowest;
             if (minVal == INFINITY) { status = GED_ERR_INFEASIBLE; break; }
+            {
+                int ties = 0, un = 0;
+                for (int it = 0; it < num_remaining; ++it)
+                    if (spc[remaining[it]] == lowest) { ++ties; if (row4col[remaining[it]] == -1) ++un; }
+                ++g_stat_steps;
+                if (ties > 1) { ++g_stat_tie_steps; if (un > 0) ++g_stat_tie_unassigned; }
+            }
             int j = remaining[index];
             if (row4col[j] == -1) sink = j; else i = row4col[j];
             SC[j] = 1;

@@ -54,6 +54,8 @@ class GedSolveDesc(ctypes.Structure):
         ("x_init", c_f32p),
         ("mat_stride", ctypes.c_int64),
         ("workspace", c_f32p),
+        ("order", c_i32p),
+        ("order_count", ctypes.c_int32),
     ]
 
 

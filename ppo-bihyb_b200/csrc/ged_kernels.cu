@@ -542,6 +542,8 @@ struct SolveParams {
     const float *x_init;
     long long mat_stride;
     float *workspace;
+    const int32_t *order;
+    int count;
     ged_solve_out out;
     SliceLayout layout;
 };
@@ -574,8 +576,9 @@ __global__ void ged_solve_kernel(SolveParams prm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (b >= prm.B) return;
+    const int slot = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (slot >= prm.count) return;
+    const int b = prm.order ? prm.order[slot] : slot;
     const Slice sm = carve(smem_raw + (size_t)warp * prm.layout.bytes, prm.layout);
     const ged_solve_out &out = prm.out;
 
@@ -974,10 +977,14 @@ int ged_solve_batch(const ged_solve_desc *d, const ged_solve_out *o, void *strea
     prm.x_init = d->x_init;
     prm.mat_stride = d->mat_stride;
     prm.workspace = d->workspace;
+    prm.order = d->order;
+    prm.count = d->order ? d->order_count : d->B;
+    if (prm.count < 0 || prm.count > d->B) return fail(GED_E_BADARG, "ged_solve_batch: order_count out of range");
+    if (prm.count == 0) return GED_OK;
     prm.out = *o;
     prm.layout = make_layout(d->pairs.max_n1, d->pairs.max_n2);
     const int S = slots_for(d->pairs.max_n1, d->pairs.max_n2);
-    GED_DISPATCH_S(S, ged_solve_kernel, prm, d->B, prm.layout.bytes, (cudaStream_t)stream, "ged_solve_batch")
+    GED_DISPATCH_S(S, ged_solve_kernel, prm, prm.count, prm.layout.bytes, (cudaStream_t)stream, "ged_solve_batch")
 }
 
 int ged_lsape_batch(int32_t B, const int32_t *n1, const int32_t *n2, int32_t max_n1, int32_t max_n2,

@@ -1,5 +1,6 @@
 """Batched entry points over the C-ABI (``include/ged_b200.h``).  Device tensors in, device tensors out, launches on
 torch's current stream, no synchronisation unless ``check=True`` asks for the per-solve status."""
+import ctypes
 from dataclasses import dataclass, field
 from typing import Optional
 
@@ -26,6 +27,7 @@ class SolveResult:
     status: torch.Tensor              # [B] int32
     x: Optional[torch.Tensor] = None  # [B, mat_stride] dense 0/1 solutions (R x C with the pair's own C)
     trace: dict = field(default_factory=dict)
+    launches: int = 0                 # ged_solve_kernel launches this call made
 
     def raise_on_error(self):
         st = self.status
@@ -48,18 +50,59 @@ def _as_i32(t, device):
     return t.to(device=device, dtype=torch.int32, non_blocking=True).contiguous()
 
 
+SIZE_CLASS_STEP = 8          # node-count granularity of the size classes (one launch per class)
+
+
+def plan_size_classes(n1: np.ndarray, n2: np.ndarray, step: int = SIZE_CLASS_STEP):
+    """Group candidates into size classes so that each launch sizes its shared-memory slice for ITS pairs, not for the
+    batch maximum (a 100-node pair needs 3x the shared memory of a 60-node pair).  Returns ``(order int32 [B],
+    classes)`` with ``classes = [(offset, count, max_n1, max_n2), ...]`` largest class first; inside a class the
+    heaviest solves come first (longest-processing-time order, so the tail of a launch is made of light solves)."""
+    n1 = np.asarray(n1, np.int64)
+    n2 = np.asarray(n2, np.int64)
+    m = np.maximum(n1, n2)
+    cls = (m + step - 1) // step
+    work = (n1 + n2) ** 3
+    order = np.lexsort((-work, -cls)).astype(np.int32)
+    classes, o = [], 0
+    sc = cls[order]
+    while o < len(order):
+        e = o
+        while e < len(order) and sc[e] == sc[o]:
+            e += 1
+        sel = order[o:e]
+        classes.append((o, e - o, max(int(n1[sel].max()), 1), max(int(n2[sel].max()), 1)))
+        o = e
+    return order, classes
+
+
+_side_streams = {}
+
+
+def _streams(dev, n):
+    pool = _side_streams.setdefault(str(dev), [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:n]
+
+
 def solve_batch(pairs: PairSet, base_idx=None, edit_u=None, edit_v=None, solver: str = "ipfp", max_iter: int = 100,
                 x_init: Optional[torch.Tensor] = None, dense_x: bool = False, trace: bool = False,
                 check: bool = False, score_adj1: Optional[torch.Tensor] = None,
-                score_adj1_off: Optional[torch.Tensor] = None, score_idx=None) -> SolveResult:
-    """All candidate solves of one batch in one launch (``ged_solve_batch``).
+                score_adj1_off: Optional[torch.Tensor] = None, score_idx=None, size_classes: bool = True,
+                plan=None) -> SolveResult:
+    """All candidate solves of one batch (``ged_solve_batch``): one launch per size class, concurrently on side
+    streams, results in candidate order.
 
     Candidate b = base pair ``base_idx[b]`` with edge ``(edit_u[b], edit_v[b])`` of graph 1 toggled
-    (reference ``GEDenv.step``, ``utils/ged_env.py:110-124``)."""
+    (reference ``GEDenv.step``, ``utils/ged_env.py:110-124``).  ``plan`` = a cached ``(order_device, classes)`` from
+    :func:`make_plan` avoids re-planning when the same candidate list is solved repeatedly."""
     lib = _lib.require_cuda()
     if solver not in SOLVERS:
         raise NotImplementedError(f"{solver} is not implemented.")      # reference ged_env.py:156
     dev = pairs.device
+    if plan is None and size_classes and not trace and x_init is None:
+        plan = make_plan(pairs, base_idx)
     base_idx = _as_i32(base_idx, dev)
     edit_u, edit_v = _as_i32(edit_u, dev), _as_i32(edit_v, dev)
     B = pairs.num_pairs if base_idx is None else int(base_idx.numel())
@@ -87,7 +130,8 @@ def solve_batch(pairs: PairSet, base_idx=None, edit_u=None, edit_v=None, solver:
     p = _lib.ptr
     desc = _lib.GedSolveDesc(pairs.c_struct(), B, p(base_idx, _lib.c_i32p), p(edit_u, _lib.c_i32p), p(edit_v, _lib.c_i32p),
                              p(score_adj1, _lib.c_u8p), p(score_adj1_off, _lib.c_i64p), p(score_idx, _lib.c_i32p),
-                             int(max_iter), SOLVERS[solver], p(x_init, _lib.c_f32p), ms, p(workspace, _lib.c_f32p))
+                             int(max_iter), SOLVERS[solver], p(x_init, _lib.c_f32p), ms, p(workspace, _lib.c_f32p),
+                             p(None, _lib.c_i32p), 0)
     out = _lib.GedSolveOut(p(res.ged, _lib.c_f32p), p(res.ged_edited, _lib.c_f32p), p(res.rowmatch, _lib.c_i32p),
                            p(res.colmatch, _lib.c_i32p), m1, m2, p(res.iters, _lib.c_i32p), p(res.status, _lib.c_i32p),
                            p(res.x, _lib.c_f32p),
@@ -96,12 +140,43 @@ def solve_batch(pairs: PairSet, base_idx=None, edit_u=None, edit_v=None, solver:
                            p(tr.get("init_cost"), _lib.c_f32p), p(tr.get("init_rowmatch"), _lib.c_i32p),
                            p(tr.get("init_colmatch"), _lib.c_i32p), p(tr.get("lap_steps"), _lib.c_u64p))
     with torch.cuda.device(dev):
-        _lib.check(lib.ged_solve_batch(desc, out, _stream(dev)), "ged_solve_batch")
+        if plan is None or len(plan[1]) <= 1:
+            _lib.check(lib.ged_solve_batch(desc, out, _stream(dev)), "ged_solve_batch")
+            res.launches = 1
+        else:
+            order_dev, classes = plan
+            cur = torch.cuda.current_stream(dev)
+            streams = _streams(dev, len(classes))
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            for (off, count, c1, c2), st in zip(classes, streams):
+                st.wait_event(ready)
+                desc.pairs.max_n1, desc.pairs.max_n2 = c1, c2
+                desc.order = ctypes.cast(ctypes.c_void_p(order_dev.data_ptr() + 4 * off), _lib.c_i32p)
+                desc.order_count = count
+                _lib.check(lib.ged_solve_batch(desc, out, st.cuda_stream), "ged_solve_batch")
+                done = torch.cuda.Event()
+                done.record(st)
+                cur.wait_event(done)
+            res.launches = len(classes)
     if workspace is not None:
         workspace.record_stream(torch.cuda.current_stream(dev))
     if check:
         res.raise_on_error()
     return res
+
+
+def make_plan(pairs: PairSet, base_idx=None):
+    """Size-class plan of a candidate list: ``(order on the device, classes)`` (see :func:`plan_size_classes`)."""
+    if base_idx is None:
+        hn1, hn2 = pairs.host_n1, pairs.host_n2
+    else:
+        hb = base_idx.detach().cpu().numpy() if torch.is_tensor(base_idx) else np.asarray(base_idx)
+        hn1, hn2 = pairs.host_n1[hb], pairs.host_n2[hb]
+    if len(hn1) == 0:
+        return None
+    order, classes = plan_size_classes(hn1, hn2)
+    return torch.from_numpy(order).to(pairs.device, non_blocking=True), classes
 
 
 def lsape_batch(cost: torch.Tensor, n1, n2, check: bool = False):
@@ -199,3 +274,44 @@ def match_to_dense(rowmatch: torch.Tensor, colmatch: torch.Tensor, n1: int, n2: 
     if n2:
         x[n1, :n2] = (colmatch[:n2] == n1).to(torch.float32)
     return x
+
+
+class HostBatch:
+    """A candidate batch in PINNED HOST memory, in the C-ABI's factor layout: what a caller of the reference-facing API
+    holds before the solve (graphs as adjacency/label pools + (base pair, u, v) per candidate)."""
+
+    def __init__(self, pairs, base_idx: np.ndarray, edit_u: np.ndarray, edit_v: np.ndarray):
+        self.tensors, self.meta = PairSet.pack_host(pairs)
+        pin = torch.cuda.is_available()
+        mk = lambda a: (torch.from_numpy(np.ascontiguousarray(a, np.int32)).pin_memory() if pin
+                        else torch.from_numpy(np.ascontiguousarray(a, np.int32)))
+        self.base_idx, self.edit_u, self.edit_v = mk(base_idx), mk(edit_u), mk(edit_v)
+        self.B = int(len(base_idx))
+        order, self.classes = plan_size_classes(self.meta["host_n1"][base_idx], self.meta["host_n2"][base_idx])
+        self.order = mk(order)
+        self.ged_host = torch.empty(self.B, dtype=torch.float32).pin_memory() if pin else torch.empty(self.B)
+
+    @property
+    def h2d_bytes(self) -> int:
+        ts = list(self.tensors.values()) + [self.base_idx, self.edit_u, self.edit_v, self.order]
+        return int(sum(t.numel() * t.element_size() for t in ts))
+
+    @property
+    def d2h_bytes(self) -> int:
+        return int(self.ged_host.numel() * self.ged_host.element_size())
+
+
+def solve_batch_host(batch: HostBatch, device, solver: str = "ipfp", max_iter: int = 100) -> torch.Tensor:
+    """End-to-end call with HOST buffers: pinned host -> device copies of the whole batch, the solve, and the
+    device -> host read of the objectives (synchronises).  Returns the pinned host tensor of B objectives."""
+    ps = PairSet.from_packed(batch.tensors, batch.meta, device)
+    base = batch.base_idx.to(device, non_blocking=True)
+    eu = batch.edit_u.to(device, non_blocking=True)
+    ev = batch.edit_v.to(device, non_blocking=True)
+    order = batch.order.to(device, non_blocking=True)
+    res = solve_batch(ps, base_idx=base, edit_u=eu, edit_v=ev, solver=solver, max_iter=max_iter,
+                      plan=(order, batch.classes))
+    batch.ged_host.copy_(res.ged, non_blocking=True)
+    torch.cuda.current_stream(device).synchronize()
+    batch.last_result = res
+    return batch.ged_host

@@ -1,0 +1,174 @@
+"""GPU: the reference-facing drop-in layer (ppo_bihyb_b200.ged_env) against the golden vectors of the unmodified
+reference and against the oracle.  Everything goes through the C-ABI."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ged_oracle as go
+from ppo_bihyb_b200 import ged_env, solver, synthetic
+from ppo_bihyb_b200.ged_env import GEDenv
+from ppo_bihyb_b200.graphs import Data, FactoredK, dense_k_from_factors, label_node_cost
+
+from _golden import load, mats_of, pairs_of
+
+pytestmark = pytest.mark.gpu
+
+
+def test_hungarian_lap_equals_reference(cuda_device):
+    """hungarian_lap (ged_env.py:329-351): pred_x identical, lb = sum(pred_x * C) as the reference computes it."""
+    z = load("lsape")
+    for t in range(len(z["n1"])):
+        n1, n2 = int(z["n1"][t]), int(z["n2"][t])
+        c = torch.from_numpy(z["cost"][z["off"][t]:z["off"][t + 1]].reshape(n1 + 1, n2 + 1).copy())
+        want = z["x"][z["off"][t]:z["off"][t + 1]].reshape(n1 + 1, n2 + 1)
+        # n1 / n2 as 1-element tensors on alternate cases, as ipfp_ged passes them (ged_env.py:262,270)
+        a1, a2 = (torch.tensor([n1]), torch.tensor([n2])) if t % 2 else (n1, n2)
+        x, lb = ged_env.hungarian_lap(c.to(cuda_device), a1, a2)
+        assert x.shape == c.shape and x.dtype == c.dtype and x.device.type == "cuda"
+        assert np.array_equal(x.cpu().numpy(), want), t
+        if np.isfinite(z["lb"][t]):
+            assert abs(float(lb) - z["lb"][t]) <= 1e-6 * max(1.0, abs(z["lb"][t]))
+        else:
+            assert not np.isfinite(float(lb))
+
+
+def test_hungarian_square_equals_scipy(cuda_device):
+    import scipy.optimize as opt
+    rng = np.random.default_rng(3)
+    s = torch.from_numpy(rng.integers(0, 4, (16, 12, 12)).astype(np.float32)).to(cuda_device)
+    perm = ged_env.hungarian(s)
+    for b in range(16):
+        row, col = opt.linear_sum_assignment(-s[b].cpu().numpy().astype(np.float64))
+        want = np.zeros((12, 12), np.float32)
+        want[row, col] = 1
+        assert np.array_equal(perm[b].cpu().numpy(), want)
+    assert ged_env.hungarian(s[0]).shape == (12, 12)
+    with pytest.raises(ValueError):
+        ged_env.hungarian(torch.zeros(3, device=cuda_device))
+    with pytest.raises(NotImplementedError):
+        ged_env.hungarian(torch.zeros(3, 4, device=cuda_device))
+
+
+def test_invalid_cost_raises_like_scipy(cuda_device):
+    c = torch.zeros(4, 4, device=cuda_device)
+    c[1, 1] = float("nan")
+    with pytest.raises(ValueError, match="invalid numeric"):
+        ged_env.hungarian_lap(c, 3, 3)
+    c = torch.full((3, 3), float("inf"), device=cuda_device)
+    with pytest.raises(ValueError, match="infeasible"):
+        ged_env.hungarian_lap(c, 2, 2)
+    with pytest.raises(AssertionError):
+        ged_env.hungarian_lap(torch.zeros(4, 4, device=cuda_device), 2, 3)
+
+
+def test_dense_k_path_equals_reference_init(cuda_device):
+    """heuristic_prediction_hun (ged_env.py:308-326) on the reference's dense K: the brute-force node_cost_mat runs as
+    one batched LSAPE launch over all rows of K and must reproduce the reference's x and lb exactly."""
+    z = load("init")
+    xs = mats_of(z, "x")
+    for p, (g1, g2) in enumerate(pairs_of(z)):
+        k = dense_k_from_factors(g1.adj, g2.adj, label_node_cost(g1.labels, g2.labels)).to(cuda_device)
+        x, lb = ged_env.heuristic_prediction_hun(k, g1.n, g2.n)
+        assert np.array_equal(x.cpu().numpy(), xs[p]) and float(lb) == z["lb"][p]
+        assert np.array_equal(ged_env.hungarian_ged(k, g1.n, g2.n).cpu().numpy(), xs[p])
+        ncm = ged_env._dense_row_costs(k, g1.n, g2.n).cpu().numpy()
+        assert np.array_equal(ncm, mats_of(z, "node_cost_mat")[p])
+
+
+def test_ipfp_ged_dense_and_factored_agree_with_oracle(cuda_device):
+    z = load("iter0")
+    env = GEDenv("ipfp", "AIDS-20-30")
+    for p, (g1, g2) in enumerate(pairs_of(z)[:5]):
+        Cn = label_node_cost(g1.labels, g2.labels)
+        o = go.solve(g1.adj, g2.adj, Cn)
+        want = go.match_to_dense(o["rowmatch"], o["colmatch"])
+        k_dense = dense_k_from_factors(g1.adj, g2.adj, Cn).to(cuda_device)
+        x = ged_env.ipfp_ged(k_dense, g1.n, g2.n)
+        assert np.array_equal(x.cpu().numpy(), want)
+        fk = env.construct_k(Data.from_host(g1), Data.from_host(g2))
+        assert isinstance(fk, FactoredK) and fk.squeeze(0) is fk and fk.shape == k_dense.shape
+        assert torch.equal(fk.dense(), k_dense)
+        x2 = ged_env.ipfp_ged(fk, torch.tensor([g1.n]), torch.tensor([g2.n]))
+        assert torch.equal(x2, x)
+        # comp_ged: dense K (HBM-bound streaming kernel) and factor form give the same integer objective
+        assert float(GEDenv.comp_ged(x, k_dense)) == o["ged"] == float(GEDenv.comp_ged(x, fk))
+        assert GEDenv.comp_ged(x, k_dense).shape == (1,)
+        xb = torch.stack([x, x2])
+        assert GEDenv.comp_ged(xb, torch.stack([k_dense, k_dense])).shape == (2,)
+
+
+def test_ipfp_ged_general_dense_k_compat_path(cuda_device):
+    """A K that is not of construct_k form takes the torch.mm + LSAPE-kernel path; on a construct_k matrix perturbed by a
+    symmetric rescaling the solution must still be a valid LSAPE matrix with objective <= the Hungarian start."""
+    g1, g2 = pairs_of(load("iter0"))[0]
+    k = dense_k_from_factors(g1.adj, g2.adj, label_node_cost(g1.labels, g2.labels)).to(cuda_device) * 1.5
+    x = ged_env.ipfp_ged(k, g1.n, g2.n, max_iter=20)
+    assert torch.all(x[:-1].sum(1) == 1) and torch.all(x[:, :-1].sum(0) == 1)
+    x0 = ged_env.hungarian_ged(k, g1.n, g2.n)
+    assert float(GEDenv.comp_ged(x, k)) <= float(GEDenv.comp_ged(x0, k))
+
+
+def test_step_matches_reference_and_oracle(cuda_device):
+    """GEDenv.step (ged_env.py:110-124): edge lists identical to the reference; reward / new_solution identical to the
+    oracle and within the aggregate contract of the reference's own (order-sensitive) trajectory."""
+    z = load("step")
+    pairs = pairs_of(z)
+    env = GEDenv("ipfp", "AIDS-20-30")
+    datas = [(Data.from_host(g1, cuda_device), Data.from_host(g2, cuda_device)) for g1, g2 in pairs]
+    ori = {p: env.solve_feasible_ged(d1, d2, "hungarian") for p, (d1, d2) in enumerate(datas)}
+    got, exact_ref = [], 0
+    B = len(z["base_idx"])
+    g1s, g2s, ks, acts, prevs = [], [], [], [], []
+    for b in range(B):
+        p = int(z["base_idx"][b])
+        ged0, k0, sec = ori[p]
+        assert float(ged0) == z["prev_solution"][b] and sec >= 0
+        act = torch.tensor([int(z["edit_u"][b]), int(z["edit_v"][b])], device=cuda_device)
+        reward, new_g1, new_sol = env.step(datas[p][0], datas[p][1], k0, act, float(ged0))
+        want_ei = z["new_edge_index"][z["new_edge_index_off"][b]:z["new_edge_index_off"][b + 1]].reshape(2, -1)
+        assert np.array_equal(new_g1.edge_index.cpu().numpy(), want_ei)
+        assert new_sol.shape == (1,) and new_sol.dtype == torch.float32 and reward.shape == (1,)
+        g1, g2 = pairs[p]
+        o = go.solve(g1.adj, g2.adj, label_node_cost(g1.labels, g2.labels), edit=(int(act[0]), int(act[1])))
+        assert new_sol.item() == o["ged"] and reward.item() == z["prev_solution"][b] - o["ged"]
+        got.append(new_sol.item())
+        exact_ref += int(new_sol.item() == z["new_solution"][b])
+        g1s.append(datas[p][0]); g2s.append(datas[p][1]); ks.append(k0); acts.append(act); prevs.append(float(ged0))
+    assert exact_ref >= B // 4
+    assert abs(np.mean(got) - z["new_solution"].mean()) <= 0.05 * z["new_solution"].mean()
+    # the batched entry point returns the same values in input order
+    rewards, new_graphs, sols = env.step_batch(g1s, g2s, ks, acts, prevs)
+    assert [s.item() for s in sols] == got
+    assert [r.item() for r in rewards] == [p - s for p, s in zip(prevs, got)]
+    # a dense ori_k (what the reference threads through) scores identically
+    p0 = int(z["base_idx"][0])
+    kd = ori[p0][1].dense()
+    r2, _, s2 = env.step(datas[p0][0], datas[p0][1], kd, acts[0], prevs[0])
+    assert s2.item() == got[0]
+
+
+def test_step_scores_on_the_original_k_after_earlier_edits(cuda_device):
+    """In beam search graph_1 already carries earlier edits while ori_k stays the ORIGINAL pair's K
+    (ged_ppo_bihyb_eval.py:23-24): the solve runs on the twice-edited pair, the score on the original."""
+    g1, g2 = synthetic.make_pairs("aids-20-30", 1, seed_offset=31)[0]
+    env = GEDenv("ipfp", "AIDS-20-30")
+    d1, d2 = Data.from_host(g1, cuda_device), Data.from_host(g2, cuda_device)
+    _, k0, _ = env.solve_feasible_ged(d1, d2, "ipfp")
+    _, d1b, _ = env.step(d1, d2, k0, torch.tensor([0, 5]), 0.0)
+    _, d1c, sol = env.step(d1b, d2, k0, torch.tensor([2, 7]), 0.0)
+    adj_b = g1.adj.copy()
+    adj_b[0, 5] = adj_b[5, 0] = 1 - adj_b[0, 5]
+    Cn = label_node_cost(g1.labels, g2.labels)
+    o = go.solve(adj_b, g2.adj, Cn, edit=(2, 7))                  # solve on (g1 + both edits)
+    assert sol.item() == go.score(g1.adj, g2.adj, Cn, o["rowmatch"], o["colmatch"])   # score on the original pair
+
+
+def test_solver_dispatch_errors(cuda_device):
+    env = GEDenv("ipfp", "AIDS-20-30")
+    g = Data.from_host(synthetic.make_pairs("aids-20-30", 1)[0][0], cuda_device)
+    with pytest.raises(NotImplementedError):
+        env.solve_feasible_ged(g, g, "rrwm")
+    bad = g.clone()
+    bad.edge_index = bad.edge_index[:, 1:]                         # one direction missing -> asymmetric adjacency
+    with pytest.raises(ValueError, match="symmetric"):
+        env.solve_feasible_ged(bad, g, "ipfp")

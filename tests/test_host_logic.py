@@ -1,0 +1,107 @@
+"""CPU: host-side logic of the drop-in layer (packing, edge toggles, factor recovery, sharding arithmetic)."""
+import numpy as np
+import pytest
+import torch
+
+from ppo_bihyb_b200 import sharding, synthetic
+from ppo_bihyb_b200.ged_env import GEDenv
+from ppo_bihyb_b200.graphs import (Data, PairSet, data_to_host, dense_k_from_factors, factors_from_dense_k,
+                                   label_node_cost, node_cost_matrix)
+
+from _golden import load, pairs_of
+
+
+def test_synthetic_graphs_have_aids_shape():
+    pairs = synthetic.make_pairs("aids-50+", 40)
+    ns = np.asarray([g.n for p in pairs for g in p])
+    assert ns.min() >= 50 and ns.max() <= 100 and 55 < ns.mean() < 65
+    for g1, g2 in pairs[:8]:
+        for g in (g1, g2):
+            assert np.array_equal(g.adj, g.adj.T) and g.adj.diagonal().sum() == 0 and g.adj.max() == 1
+            deg = g.adj.sum(1)
+            assert deg.max() <= synthetic.MAX_DEGREE and 0.95 * g.n <= g.adj.sum() / 2 <= 1.2 * g.n
+            assert g.features().shape == (g.n, 34)
+    again = synthetic.make_pairs("aids-50+", 40)
+    assert all(np.array_equal(a[0].adj, b[0].adj) and np.array_equal(a[1].labels, b[1].labels) for a, b in zip(pairs, again))
+
+
+def test_pack_host_layout_is_the_c_struct_layout():
+    pairs = synthetic.make_pairs("aids-20-30", 5)
+    t, meta = PairSet.pack_host(pairs)
+    assert meta["max_n1"] == max(g1.n for g1, _ in pairs) and meta["max_n2"] == max(g2.n for _, g2 in pairs)
+    for p, (g1, g2) in enumerate(pairs):
+        o = int(t["adj1_off"][p])
+        assert np.array_equal(t["adj1"][o:o + g1.n ** 2].numpy().reshape(g1.n, g1.n), g1.adj)
+        o = int(t["lab2_off"][p])
+        assert np.array_equal(t["lab2"][o:o + g2.n].numpy(), g2.labels)
+    assert t["adj1"].dtype == torch.uint8 and t["n1"].dtype == torch.int32 and t["adj1_off"].dtype == torch.int64
+
+
+def test_data_round_trip_and_label_recovery():
+    g = synthetic.make_pairs("aids-20-30", 1)[0][0]
+    d = Data.from_host(g)
+    adj, labels, feat = data_to_host(d, synthetic.NUM_LABELS)
+    assert np.array_equal(adj, g.adj) and np.array_equal(labels, g.labels) and feat.shape[1] == 29
+    # non one-hot features: labels cannot be recovered, the explicit node-cost matrix is used instead
+    d.x = d.x.clone()
+    d.x[0, :29] = 0
+    _, labels, feat = data_to_host(d, synthetic.NUM_LABELS)
+    assert labels is None
+    cost = node_cost_matrix(feat, feat)
+    assert cost.shape == (g.n + 1, g.n + 1) and cost[0, 0] == 0 and cost[-1, -1] == 0 and cost[0, -1] == 0
+
+
+def test_toggle_edge_matches_reference_step_edge_lists():
+    """GEDenv.step's edit (ged_env.py:111-121) against the reference's new edge_index, element for element."""
+    z = load("step")
+    pairs = pairs_of(z)
+    for b in range(len(z["base_idx"])):
+        g1 = pairs[z["base_idx"][b]][0]
+        d = Data.from_host(g1)
+        before = d.edge_index.clone()
+        out = GEDenv.toggle_edge(d, torch.tensor([int(z["edit_u"][b]), int(z["edit_v"][b])]))
+        want = z["new_edge_index"][z["new_edge_index_off"][b]:z["new_edge_index_off"][b + 1]].reshape(2, -1)
+        assert np.array_equal(out.edge_index.numpy(), want)
+        assert torch.equal(d.edge_index, before)                    # input untouched (reference clones, :111)
+
+
+def test_factor_recovery_from_dense_k():
+    g1, g2 = synthetic.make_pairs("aids-20-30", 1)[0]
+    Cn = label_node_cost(g1.labels, g2.labels)
+    k = dense_k_from_factors(g1.adj, g2.adj, Cn)
+    assert torch.equal(k, k.T)
+    a1, a2, cost = factors_from_dense_k(k, g1.n, g2.n)
+    assert np.array_equal(a1, g1.adj) and np.array_equal(a2, g2.adj) and np.array_equal(cost, Cn)
+
+
+def test_unknown_solver_and_dataset_errors():
+    with pytest.raises(AssertionError):
+        GEDenv(solver_type="rrwm")
+    env = GEDenv("ipfp", "AIDS-20-30")
+    g = Data.from_host(synthetic.make_pairs("aids-20-30", 1)[0][0])
+    with pytest.raises(NotImplementedError):
+        env.solve_feasible_ged(g, g, "nope")
+    with pytest.raises(ValueError):
+        GEDenv.comp_ged(torch.zeros(2), torch.zeros(2, 2))
+
+
+def test_shard_indices_partition_and_balance():
+    rng = np.random.default_rng(0)
+    for B, world in ((0, 2), (5, 8), (4096, 8), (1000, 3)):
+        n1, n2 = rng.integers(50, 101, B), rng.integers(50, 101, B)
+        for cost in (None, sharding.work_estimate(n1, n2)):
+            parts = [sharding.shard_indices(B, r, world, cost) for r in range(world)]
+            allidx = np.concatenate(parts) if parts else np.zeros(0, np.int64)
+            assert np.array_equal(np.sort(allidx), np.arange(B))
+            assert max(len(p) for p in parts) <= -(-B // world) if B else True
+        if B >= 1000:
+            w = sharding.work_estimate(n1, n2)
+            loads = [w[sharding.shard_indices(B, r, world, w)].sum() for r in range(world)]
+            assert max(loads) / (sum(loads) / world) < 1.02
+
+
+def test_gather_results_single_process():
+    local = torch.arange(6, dtype=torch.float32)
+    idx = np.asarray([5, 0, 3, 1, 4, 2])
+    out = sharding.gather_results(local, idx, 6)
+    assert torch.equal(out[torch.as_tensor(idx)], local)

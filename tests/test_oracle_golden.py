@@ -142,3 +142,22 @@ def test_step_reward_against_reference():
     assert np.array_equal(z["prev_solution"] - z["new_solution"], z["reward"])
     assert abs(got.mean() - z["new_solution"].mean()) <= 0.05 * z["new_solution"].mean()
     assert exact >= len(got) // 4
+
+
+def test_closed_form_init_holds_for_arbitrary_node_costs_and_dense_graphs():
+    """The degree closed form of heuristic_prediction_hun's node_cost_mat must not depend on the node
+    costs or on the graphs being molecule-like: brute force (one LSAPE per row of K, as ged_env.py:310-313) vs closed form."""
+    from ppo_bihyb_b200 import synthetic
+    rng = np.random.default_rng(77)
+    for t in range(40):
+        n1, n2 = int(rng.integers(1, 9)), int(rng.integers(1, 9))
+        if t % 2:
+            g1, g2 = synthetic.molecule_like(n1, rng), synthetic.molecule_like(n2, rng)
+            a1, a2 = g1.adj, g2.adj
+        else:
+            a1 = np.triu(rng.integers(0, 2, (n1, n1)), 1)
+            a1 = (a1 + a1.T).astype(np.uint8)
+            a2 = np.triu(rng.integers(0, 2, (n2, n2)), 1)
+            a2 = (a2 + a2.T).astype(np.uint8)
+        Cn = (rng.integers(0, 5, (n1 + 1, n2 + 1)) * 0.5).astype(np.float32)
+        assert np.array_equal(go.init_cost_closed_form(a1, a2), go.init_cost_bruteforce(a1, a2, Cn)), t
