@@ -61,7 +61,7 @@ __host__ __device__ inline SliceLayout make_layout(int max_n1, int max_n2)
     SliceLayout L;
     int o = 0;
     L.off_u = o;        o += 8 * Nm;
-    L.off_cost = o;     o += 4 * Rm * Cm;
+    L.off_cost = o;     o += 4 * (Rm * Cm + 32 * ((Cm + 31) / 32));   // + one padded row: lanes read past C
     L.off_bits1 = o;    o += 4 * Rm * W1;
     L.off_bits2 = o;    o += 4 * Cm * W2;
     L.off_rs = o;       o += 4 * Rm;
@@ -175,6 +175,95 @@ __device__ __forceinline__ bool bit_at(const uint32_t *bits, int W, int i, int j
 // selection rule "last minimum whose column is unassigned, else first minimum" becomes a lexicographic arg-min
 // over (spc, key) with key = unassigned ? -1-pos : pos, done with three integer warp reductions.
 // ---------------------------------------------------------------------------------------------------------------
+// Order-preserving map double -> (hi, lo) unsigned pair (and back), so that a 64-bit floating-point minimum becomes two
+// 32-bit integer warp reductions.  -0.0 cannot occur among the reduced costs (minVal starts at +0.0 and x - x = +0.0 in
+// round-to-nearest), so the map agrees with IEEE comparison on every value it sees.
+__device__ __forceinline__ void ord_from_double(double x, unsigned &ohi, unsigned &olo)
+{
+    const unsigned hi = (unsigned)__double2hiint(x), lo = (unsigned)__double2loint(x);
+    const unsigned neg = (unsigned)((int)hi >> 31);
+    ohi = hi ^ (neg | 0x80000000u);
+    olo = lo ^ neg;
+}
+__device__ __forceinline__ double double_from_ord(unsigned ohi, unsigned olo)
+{
+    const unsigned pos = (unsigned)((int)ohi >> 31);          // all ones for originally non-negative values
+    return __hiloint2double((int)(ohi ^ (~pos | 0x80000000u)), (int)(olo ^ ~pos));
+}
+
+// ---- per-slot building blocks of the LAP scan step, written as PTX so that each is exactly the intended handful of
+// SASS instructions (LOP3 -> predicate, DSETP with the predicate folded in, selects) without moves or branches -----------
+
+// if (live & MASK) && r < spc:  spc = r, pth = i, improved = 1
+template <unsigned MASK>
+__device__ __forceinline__ void lap_relax(double &spc, int &pth, int &improved, double r, int i, unsigned live)
+{
+    asm("{\n\t.reg .pred q, p;\n\t.reg .b32 t;\n\t"
+        "and.b32 t, %5, %6;\n\t"
+        "setp.ne.u32 q, t, 0;\n\t"
+        "setp.lt.and.f64 p, %3, %0, q;\n\t"
+        "selp.f64 %0, %3, %0, p;\n\t"
+        "selp.b32 %1, %4, %1, p;\n\t"
+        "@p mov.b32 %2, 1;\n\t}"
+        : "+d"(spc), "+r"(pth), "+r"(improved) : "d"(r), "r"(i), "r"(live), "n"(MASK));
+}
+// if (live & MASK) && spc < lm:  lm = spc
+template <unsigned MASK>
+__device__ __forceinline__ void lap_min_value(double &lm, double spc, unsigned live)
+{
+    asm("{\n\t.reg .pred q, p;\n\t.reg .b32 t;\n\t"
+        "and.b32 t, %2, %3;\n\t"
+        "setp.ne.u32 q, t, 0;\n\t"
+        "setp.lt.and.f64 p, %1, %0, q;\n\t"
+        "selp.f64 %0, %1, %0, p;\n\t}"
+        : "+d"(lm) : "d"(spc), "r"(live), "n"(MASK));
+}
+// if (live & MASK) && spc == minVal:  lk = min(lk, posk ^ kx)
+template <unsigned MASK>
+__device__ __forceinline__ void lap_min_key(unsigned &lk, double spc, double minVal, unsigned live, int posk, int kx)
+{
+    asm("{\n\t.reg .pred q, p;\n\t.reg .b32 t, k;\n\t"
+        "and.b32 t, %3, %4;\n\t"
+        "setp.ne.u32 q, t, 0;\n\t"
+        "setp.eq.and.f64 p, %1, %2, q;\n\t"
+        "xor.b32 k, %5, %6;\n\t"
+        "selp.b32 k, k, 0xffffffff, p;\n\t"
+        "min.u32 %0, %0, k;\n\t}"
+        : "+r"(lk) : "d"(spc), "d"(minVal), "r"(live), "n"(MASK), "r"(posk), "r"(kx));
+}
+
+template <int S, int I = 0>
+struct LapSlots {
+    static __device__ __forceinline__ void relax_range(double (&spc)[2 * S], int (&pth)[2 * S], int &improved,
+                                                       const double (&v)[2 * S], double base, int i, unsigned live, int lo, int hi)
+    {
+        if constexpr (I < 2 * S) {
+            if (I >= lo && I < hi) lap_relax<(1u << I)>(spc[I], pth[I], improved, __dsub_rn(base, v[I]), i, live);
+            LapSlots<S, I + 1>::relax_range(spc, pth, improved, v, base, i, live, lo, hi);
+        }
+    }
+    static __device__ __forceinline__ void min_value(double &lm, const double (&spc)[2 * S], unsigned live)
+    {
+        if constexpr (I < 2 * S) {
+            lap_min_value<(1u << I)>(lm, spc[I], live);
+            LapSlots<S, I + 1>::min_value(lm, spc, live);
+        }
+    }
+    static __device__ __forceinline__ void min_key(unsigned &lk, const double (&spc)[2 * S], double minVal, unsigned live,
+                                                   const int (&posk)[2 * S], const int (&kx)[2 * S])
+    {
+        if constexpr (I < 2 * S) {
+            lap_min_key<(1u << I)>(lk, spc[I], minVal, live, posk[I], kx[I]);
+            LapSlots<S, I + 1>::min_key(lk, spc, minVal, live, posk, kx);
+        }
+    }
+};
+
+// LSAPE through the expanded (n1+n2)^2 LAP in SciPy's order (hungarian_lap ged_env.py:329-351; scipy rectangular_lsap).
+// Columns live in registers, one per (lane, slot): real column a -> lane a & 31, slot a >> 5; deletion column n2+k ->
+// lane k & 31, slot S + (k >> 5).  Tie-break key of a column:  kk << 17 | slot << 14 | lane << 9 | (row4col + 1), with
+// kk = pos ^ 511 for an unassigned column (SciPy: the LAST unassigned minimum wins) and pos ^ 512 = 512 + pos for an
+// assigned one (else the FIRST minimum wins); pos = index in SciPy's `remaining` vector.  The smallest key wins.
 template <int S>
 __device__ int lsape_warp(const float *cost, int n1, int n2, const Slice &sm, unsigned long long *steps_out)
 {
@@ -192,13 +281,13 @@ __device__ int lsape_warp(const float *cost, int n1, int n2, const Slice &sm, un
     }
 
     double v[2 * S];
-    unsigned invalid = 0;                    // bit s set: slot s has no column
+    unsigned exist = 0;                      // bit s set: this lane's slot s holds a column of the expanded matrix
 #pragma unroll
     for (int s = 0; s < S; ++s) {
         v[s] = 0.0;
         v[S + s] = 0.0;
-        if (lane + 32 * s >= n2) invalid |= 1u << s;
-        if (lane + 32 * s >= n1) invalid |= 1u << (S + s);
+        if (lane + 32 * s < n2) exist |= 1u << s;
+        if (lane + 32 * s < n1) exist |= 1u << (S + s);
     }
     for (int t = lane; t < N; t += 32) { u[t] = 0.0; sm.row4col[t] = -1; sm.col4row[t] = -1; }
     __syncwarp();
@@ -206,113 +295,101 @@ __device__ int lsape_warp(const float *cost, int n1, int n2, const Slice &sm, un
     unsigned long long steps = 0;
     for (int cur = 0; cur < N; ++cur) {
         double spc[2 * S];
-        int pth[2 * S], pos[2 * S], stat[2 * S];      // stat = (column id << 9) | (row4col + 1)
-        unsigned assigned = 0;
+        int pth[2 * S], posk[2 * S], kx[2 * S];
 #pragma unroll
         for (int s = 0; s < 2 * S; ++s) {
             const int j = (s < S) ? (lane + 32 * s) : (n2 + lane + 32 * (s - S));
             spc[s] = INFINITY;
             pth[s] = -1;
-            pos[s] = N - 1 - j;
+            posk[s] = (N - 1 - j) << 17;
             int r4 = -1;
-            if (!((invalid >> s) & 1u)) r4 = sm.row4col[j];
-            if (r4 >= 0) assigned |= 1u << s;
-            stat[s] = (j << 9) | (r4 + 1);
+            if ((exist >> s) & 1u) r4 = sm.row4col[j];
+            kx[s] = (((r4 >= 0) ? 512 : 511) << 17) | (s << 14) | (lane << 9) | (r4 + 1);
+            asm volatile("" : "+r"(kx[s]));          // keep it in a register (no re-derivation inside the scan loop)
         }
-        unsigned sc = invalid;               // removed-from-`remaining` mask (SC plus non-existent slots)
+        unsigned live = exist;               // columns still in `remaining`
         double minVal = 0.0;
-        int i = cur, sink = -1, num_remaining = N;
+        int i = cur, lastk = N << 17;
+        unsigned mk;
+        int nsteps = 0;
 
-        while (sink < 0) {
-            ++steps;
+        for (;;) {
+            ++nsteps;
             const double ui = u[i];
+            int improved = 0;
             if (i < n1) {                    // real row: n2 substitution entries + its own deletion entry
                 const float *crow = cost + i * C;
 #pragma unroll
-                for (int s = 0; s < S; ++s)
-                    if (!((sc >> s) & 1u)) {
-                        const double c = (double)crow[lane + 32 * s];
-                        const double r = __dsub_rn(__dsub_rn(__dadd_rn(minVal, c), ui), v[s]);
-                        if (r < spc[s]) { spc[s] = r; pth[s] = i; }
-                    }
-                {   // one-hot slot mask instead of `s == i >> 5`: keeps the per-slot state in registers
-                    const unsigned hit = ((lane == (i & 31)) ? (1u << (i >> 5)) : 0u) & ~(sc >> S);
-                    const double c = (double)crow[n2];
-#pragma unroll
-                    for (int s = 0; s < S; ++s)
-                        if ((hit >> s) & 1u) {
-                            const double r = __dsub_rn(__dsub_rn(__dadd_rn(minVal, c), ui), v[S + s]);
-                            if (r < spc[S + s]) { spc[S + s] = r; pth[S + s] = i; }
-                        }
+                for (int s = 0; s < S; ++s) {
+                    const double c = (double)crow[lane + 32 * s];
+                    const double r = __dsub_rn(__dsub_rn(__dadd_rn(minVal, c), ui), v[s]);
+                    if (s == 0) lap_relax<1u>(spc[0], pth[0], improved, r, i, live);
+                    if (s == 1) lap_relax<2u>(spc[s], pth[s], improved, r, i, live);
+                    if (s == 2) lap_relax<4u>(spc[s], pth[s], improved, r, i, live);
+                    if (s == 3) lap_relax<8u>(spc[s], pth[s], improved, r, i, live);
+                    if (s == 4) lap_relax<16u>(spc[s], pth[s], improved, r, i, live);
+                    if (s == 5) lap_relax<32u>(spc[s], pth[s], improved, r, i, live);
+                    if (s == 6) lap_relax<64u>(spc[s], pth[s], improved, r, i, live);
                 }
+                const double rd = __dsub_rn(__dadd_rn(minVal, (double)crow[n2]), ui);
+                const unsigned hl = (lane == (i & 31)) ? (live & ((1u << S) << (i >> 5))) : 0u;
+                LapSlots<S>::relax_range(spc, pth, improved, v, rd, i, hl, S, 2 * S);
             } else {                         // insertion row of column a0: its own entry + the zero block
                 const int a0 = i - n1;
-                {
-                    const unsigned hit = ((lane == (a0 & 31)) ? (1u << (a0 >> 5)) : 0u) & ~sc;
-                    const double c = (double)cost[n1 * C + a0];
-#pragma unroll
-                    for (int s = 0; s < S; ++s)
-                        if ((hit >> s) & 1u) {
-                            const double r = __dsub_rn(__dsub_rn(__dadd_rn(minVal, c), ui), v[s]);
-                            if (r < spc[s]) { spc[s] = r; pth[s] = i; }
-                        }
-                }
-                const double base = __dsub_rn(__dadd_rn(minVal, 0.0), ui);
-#pragma unroll
-                for (int s = S; s < 2 * S; ++s)
-                    if (!((sc >> s) & 1u)) {
-                        const double r = __dsub_rn(base, v[s]);
-                        if (r < spc[s]) { spc[s] = r; pth[s] = i; }
-                    }
+                const double ra = __dsub_rn(__dadd_rn(minVal, (double)cost[n1 * C + a0]), ui);
+                const unsigned hl = (lane == (a0 & 31)) ? (live & (1u << (a0 >> 5))) : 0u;
+                LapSlots<S>::relax_range(spc, pth, improved, v, ra, i, hl, 0, S);
+                const double rz = __dsub_rn(__dadd_rn(minVal, 0.0), ui);
+                LapSlots<S>::relax_range(spc, pth, improved, v, rz, i, live, S, 2 * S);
             }
 
-            // lexicographic arg-min over (spc, key): lane-local first, then across the warp
-            double bd = INFINITY;
-            unsigned bk = 0xffffffffu;
-#pragma unroll
-            for (int s = 0; s < 2 * S; ++s)
-                if (!((sc >> s) & 1u)) {
-                    const unsigned kk = ((assigned >> s) & 1u) ? (unsigned)(N + pos[s]) : (unsigned)(N - 1 - pos[s]);
-                    const unsigned packed = (kk << 18) | (unsigned)stat[s];
-                    if (spc[s] < bd || (spc[s] == bd && packed < bk)) { bd = spc[s]; bk = packed; }
-                }
-            const long long bits = __double_as_longlong(bd);
-            const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
-            const unsigned neg = (unsigned)((int)hi >> 31);
-            const unsigned ohi = hi ^ (neg | 0x80000000u), olo = lo ^ neg;
-            const unsigned mhi = __reduce_min_sync(kFull, ohi);
-            const unsigned mlo = __reduce_min_sync(kFull, ohi == mhi ? olo : 0xffffffffu);
-            const unsigned mk = __reduce_min_sync(kFull, (ohi == mhi && olo == mlo) ? bk : 0xffffffffu);
-            {
-                const unsigned rhi = (mhi & 0x80000000u) ? (mhi ^ 0x80000000u) : ~mhi;
-                const unsigned rlo = (mhi & 0x80000000u) ? mlo : ~mlo;
-                minVal = __longlong_as_double((long long)(((unsigned long long)rhi << 32) | rlo));
+            // If no shortest-path cost changed, the minimum over the remaining columns is still minVal as long as one
+            // of them attains it: go straight to the tie-break (pass 2); otherwise recompute the minimum (pass 1).
+            unsigned lk = 0xffffffffu;
+            bool need_min = __any_sync(kFull, improved != 0);
+            if (!need_min) {
+                LapSlots<S>::min_key(lk, spc, minVal, live, posk, kx);
+                mk = __reduce_min_sync(kFull, lk);
+                need_min = (mk == 0xffffffffu);
             }
-            if (minVal == INFINITY) return GED_ST_INFEASIBLE;
+            if (need_min) {
+                double lm = INFINITY;
+                LapSlots<S>::min_value(lm, spc, live);
+                unsigned ohi, olo;
+                ord_from_double(lm, ohi, olo);
+                const unsigned mhi = __reduce_min_sync(kFull, ohi);
+                const unsigned mlo = __reduce_min_sync(kFull, ohi == mhi ? olo : 0xffffffffu);
+                minVal = double_from_ord(mhi, mlo);
+                if (minVal == INFINITY) return GED_ST_INFEASIBLE;
+                lk = 0xffffffffu;
+                LapSlots<S>::min_key(lk, spc, minVal, live, posk, kx);
+                mk = __reduce_min_sync(kFull, lk);
+            }
 
-            const int jstar = (int)((mk >> 9) & 511u);
+            // the winning column leaves `remaining`; the column at its end takes the freed position
+            lastk -= 1 << 17;
+            const int posstark = (int)((mk & 0xfffe0000u) ^ ((mk & (512u << 17)) ? (512u << 17) : (511u << 17)));
+            if (lk == mk) live &= ~(1u << ((mk >> 14) & 7u));
+#pragma unroll
+            for (int s = 0; s < 2 * S; ++s) posk[s] = (posk[s] == lastk) ? posstark : posk[s];
             const int r4star = (int)(mk & 511u) - 1;
-            const int kkstar = (int)(mk >> 18);
-            const int posstar = (kkstar >= N) ? (kkstar - N) : (N - 1 - kkstar);
-            const int last = --num_remaining;
-            // owner marks the column as scanned; the column that sat at `last` moves into the freed position
-            const int ls = (jstar < n2) ? jstar : (jstar - n2);
-            const int slotstar = (jstar < n2) ? (ls >> 5) : (S + (ls >> 5));
-            if (lane == (ls & 31)) sc |= 1u << slotstar;
-#pragma unroll
-            for (int s = 0; s < 2 * S; ++s) pos[s] = (pos[s] == last) ? posstar : pos[s];
-            if (r4star < 0) sink = jstar; else i = r4star;
+            if (r4star < 0) break;
+            i = r4star;
         }
+        steps += nsteps;
+        const int wl = (int)((mk >> 9) & 31u), ws = (int)((mk >> 14) & 7u);
+        const int sink = (ws < S) ? (wl + 32 * ws) : (n2 + wl + 32 * (ws - S));
 
-        // dual update (scipy solve(): u[cur] += minVal; u[i] += minVal - spc[col4row[i]]; v[j] -= minVal - spc[j])
+        // dual update (scipy solve(): u[cur] += minVal; u[i] += minVal - spc[col4row[i]]; v[j] -= minVal - spc[j]);
+        // a removed column's spc is frozen at the minimum of the step that removed it
 #pragma unroll
         for (int s = 0; s < 2 * S; ++s) {
-            const bool scanned = ((sc >> s) & 1u) && !((invalid >> s) & 1u);
+            const bool scanned = ((exist & ~live) >> s) & 1u;
             if (scanned) {
                 const int j = (s < S) ? (lane + 32 * s) : (n2 + lane + 32 * (s - S));
                 const double delta = __dsub_rn(minVal, spc[s]);
                 v[s] = __dsub_rn(v[s], delta);
-                const int r4 = (stat[s] & 511) - 1;
+                const int r4 = (kx[s] & 511) - 1;
                 if (j != sink) u[r4] = __dadd_rn(u[r4], delta);
                 sm.path[j] = (int16_t)pth[s];
             }
@@ -909,7 +986,9 @@ int launch_sized(KernelT kernel, const ParamsT &prm, int count, int slice_bytes,
 {
     int wpb = warps_per_block_for(slice_bytes);
     while (wpb > 1 && (long long)wpb * slice_bytes > kMaxSmemBytes) --wpb;
-    const int smem = wpb * slice_bytes;
+    static int pad = -1;                    // occupancy experiments only: extra dynamic shared memory per CTA
+    if (pad < 0) { const char *e = getenv("GED_B200_SMEM_PAD"); pad = e ? atoi(e) : 0; }
+    const int smem = wpb * slice_bytes + pad;
     if (smem > kMaxSmemBytes) return fail(GED_E_TOO_LARGE, "pair too large for one warp's shared-memory slice");
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail_cuda(e, name);
