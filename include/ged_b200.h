@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GED_ABI_VERSION 1
+#define GED_ABI_VERSION 2
 
 /* call-level errors */
 #define GED_OK 0
@@ -77,7 +77,7 @@ typedef struct ged_solve_desc {
     const float *x_init;
     int64_t mat_stride;      /* elements between consecutive candidates in x_init / x_out / workspace / trace;
                                 must be >= (max_n1+1)*(max_n2+1) */
-    float *workspace;        /* B * mat_stride floats of scratch (the fractional iterate lives here, L2 resident) */
+    float *workspace;        /* 2 * B * mat_stride floats of scratch: per candidate the fractional iterate X and X*A2^T (L2 resident) */
     /* Optional sub-launch: solve only candidates order[0 .. order_count) (indices into the B candidates; results are
      * still written at the candidate's own index).  The host layer uses this to launch one size class at a time with
      * that class's max_n1/max_n2, so that shared memory per solve follows the pair's size, not the batch maximum. */

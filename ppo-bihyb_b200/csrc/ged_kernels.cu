@@ -116,6 +116,7 @@ __device__ inline Slice carve(unsigned char *base, const SliceLayout &L)
 // Per-pair view used by the math routines.
 struct Pair {
     int n1, n2, R, C, N, W1, W2;
+    int maxdeg;                 // max node degree over both graphs (after the candidate edit)
     const float *node_cost;     // global, R x C, or nullptr -> label metric
 };
 
@@ -424,7 +425,7 @@ __device__ int lsape_warp(const float *cost, int n1, int n2, const Slice &sm, un
 // T = number of 32-wide column tiles of a row.
 // ---------------------------------------------------------------------------------------------------------------
 template <int S>
-__device__ void kv_apply(const Pair &P, const Slice &sm, const float *X, float *cost)
+__device__ void kv_apply_generic(const Pair &P, const Slice &sm, const float *X, float *cost)
 {
     constexpr int T = S + 1;
     const int lane = threadIdx.x & 31;
@@ -508,6 +509,121 @@ __device__ void kv_apply(const Pair &P, const Slice &sm, const float *X, float *
     __syncwarp();
 }
 
+// Fast path of K vec(X) for graphs whose maximum degree is <= kMaxDeg (molecules: <= 4, +1 for a candidate edit).
+// Same arithmetic, same summation order as kv_apply_generic (and oracle/ged_oracle.c), restructured around
+//     Y = X A2^T   (Y[j,a] = sum_{b in N2(a)} X[j,b], ascending b)
+// so that every inner term is a ROW gather:  P[i,a] = sum_{j in N1(i)} X[j,a],  T3[i,a] = sum_{j in N1(i)} Y[j,a],
+// Q[i,a] = Y[i,a].  X is staged once in the (not yet written) cost region of shared memory for the random column
+// gathers of Y; Y goes to global scratch; the final pass reads X and Y rows with coalesced, mutually independent loads
+// (one L2 round trip per row of the result) and writes cost into shared memory.
+constexpr int kMaxDeg = 6;
+
+__device__ __forceinline__ void decode_neighbours(const uint32_t *row, int W, int (&nb)[kMaxDeg])
+{
+    int w = 0;
+    uint32_t word = row[0];
+#pragma unroll
+    for (int k = 0; k < kMaxDeg; ++k) {
+        while (word == 0u && w + 1 < W) word = row[++w];
+        nb[k] = word ? (w * 32 + __ffs(word) - 1) : -1;
+        word &= word - 1u;
+    }
+}
+
+template <int S>
+__device__ void kv_apply(const Pair &P, const Slice &sm, const float *X, float *Y, float *cost)
+{
+    if (P.maxdeg > kMaxDeg) { kv_apply_generic<S>(P, sm, X, cost); return; }
+    constexpr int T = S + 1;
+    const int lane = threadIdx.x & 31;
+    const int R = P.R, C = P.C, n1 = P.n1, n2 = P.n2, RC = R * C;
+
+    for (int e = lane; e < RC; e += 32) cost[e] = X[e];          // stage X
+    __syncwarp();
+
+    float csacc[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) csacc[t] = 0.0f;
+    for (int i = 0; i < R; ++i) {
+        float part = 0.0f;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const int a = lane + 32 * t;
+            if (a < C) {
+                const float x = cost[i * C + a];
+                csacc[t] = __fadd_rn(csacc[t], x);
+                part = __fadd_rn(part, x);
+            }
+        }
+        part = warp_butterfly(part);
+        if (lane == 0) sm.rs[i] = part;
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) { const int a = lane + 32 * t; if (a < C) sm.cs[a] = csacc[t]; }
+    __syncwarp();
+    for (int i = lane; i < R; i += 32) {
+        int nb[kMaxDeg];
+        decode_neighbours(sm.bits1 + i * P.W1, P.W1, nb);
+        float s = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kMaxDeg; ++k) if (nb[k] >= 0) s = __fadd_rn(s, sm.rs[nb[k]]);
+        sm.rsP[i] = s;
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        if (32 * t >= C) break;
+        const int a = lane + 32 * t;
+        if (a < C) {
+            int nb[kMaxDeg];
+            decode_neighbours(sm.bits2 + a * P.W2, P.W2, nb);
+            float s = 0.0f;
+#pragma unroll
+            for (int k = 0; k < kMaxDeg; ++k) if (nb[k] >= 0) s = __fadd_rn(s, sm.cs[nb[k]]);
+            sm.csQ[a] = s;
+            for (int j = 0; j < R; ++j) {                        // Y[j, a]
+                const float *xr = cost + j * C;
+                float in = 0.0f;
+#pragma unroll
+                for (int k = 0; k < kMaxDeg; ++k) if (nb[k] >= 0) in = __fadd_rn(in, xr[nb[k]]);
+                Y[j * C + a] = in;
+            }
+        }
+    }
+    __syncwarp();
+
+    for (int i = 0; i < R; ++i) {
+        int nb[kMaxDeg];
+        decode_neighbours(sm.bits1 + i * P.W1, P.W1, nb);        // warp-uniform
+        const float rsPi = sm.rsP[i];
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            if (32 * t >= C) break;
+            const int a = lane + 32 * t;
+            if (a < C) {
+                float xv[kMaxDeg], yv[kMaxDeg];
+#pragma unroll
+                for (int k = 0; k < kMaxDeg; ++k) {              // all loads first: they are independent
+                    xv[k] = 0.0f;
+                    yv[k] = 0.0f;
+                    if (nb[k] >= 0) { xv[k] = X[nb[k] * C + a]; yv[k] = Y[nb[k] * C + a]; }
+                }
+                const float xia = X[i * C + a], Qv = Y[i * C + a];
+                float Pv = 0.0f, T3 = 0.0f;
+#pragma unroll
+                for (int k = 0; k < kMaxDeg; ++k)
+                    if (nb[k] >= 0) { Pv = __fadd_rn(Pv, xv[k]); T3 = __fadd_rn(T3, yv[k]); }
+                const float t1 = (a < n2) ? __fsub_rn(rsPi, Pv) : rsPi;
+                const float t2 = (i < n1) ? __fsub_rn(sm.csQ[a], Qv) : sm.csQ[a];
+                float sres = __fadd_rn(t1, t2);
+                sres = __fsub_rn(sres, __fadd_rn(T3, T3));
+                const float d = __fmul_rn(node_cost_at(P, sm, i, a), xia);
+                cost[i * C + a] = __fadd_rn(sres, d);
+            }
+        }
+    }
+    __syncwarp();
+}
+
 // <A, B> over the flat R*C index, fp64: lane-strided partials + butterfly.
 __device__ inline double dot_flat(const float *a_smem, const float *b_glob, int n)
 {
@@ -560,6 +676,16 @@ __device__ inline double score_assignment(const Pair &P, const Slice &sm, int nn
     preserved = __reduce_add_sync(kFull, preserved);
     const double nodes = matched_sum(P, sm, nullptr, rowmatch, colmatch);
     return __dadd_rn(nodes, (double)(nnz1 + nnz2 - 2 * preserved));
+}
+
+// maximum row popcount over both bit-packed adjacencies (warp-uniform)
+__device__ inline int max_degree(const uint32_t *bits1, int R, int W1, const uint32_t *bits2, int C, int W2)
+{
+    const int lane = threadIdx.x & 31;
+    int m = 0;
+    for (int i = lane; i < R; i += 32) { int d = 0; for (int w = 0; w < W1; ++w) d += __popc(bits1[i * W1 + w]); m = max(m, d); }
+    for (int a = lane; a < C; a += 32) { int d = 0; for (int w = 0; w < W2; ++w) d += __popc(bits2[a * W2 + w]); m = max(m, d); }
+    return __reduce_max_sync(kFull, m);
 }
 
 __device__ inline int count_bits(const uint32_t *bits, int words)
@@ -682,8 +808,10 @@ __global__ void ged_solve_kernel(SolveParams prm)
         __syncwarp();
     }
     const int nnz1 = count_bits(sm.bits1, P.R * P.W1), nnz2 = count_bits(sm.bits2, P.C * P.W2);
+    P.maxdeg = max_degree(sm.bits1, P.R, P.W1, sm.bits2, P.C, P.W2);
 
-    float *X = prm.workspace + (long long)b * prm.mat_stride;
+    float *X = prm.workspace + (long long)b * 2 * prm.mat_stride;        // fractional iterate
+    float *Y = X + prm.mat_stride;                                       // X A2^T scratch of kv_apply
     unsigned long long lap_steps = 0;
     int iters = 0;
     double best_ub = INFINITY;
@@ -722,7 +850,7 @@ __global__ void ged_solve_kernel(SolveParams prm)
     if (status == 0 && prm.solver_kind == GED_SOLVER_IPFP) {
         for (int it = 0; it < prm.max_iter; ++it) {
             iters = it + 1;
-            kv_apply<S>(P, sm, X, sm.cost);                              // ged_env.py:269
+            kv_apply<S>(P, sm, X, Y, sm.cost);                           // ged_env.py:269
             const double s_vv = dot_flat(sm.cost, X, RC);                // = last_v^T K last_v, ged_env.py:283
             if (out.tr_cost) {
                 float *dst = out.tr_cost + ((long long)b * prm.max_iter + it) * prm.mat_stride;
@@ -867,8 +995,10 @@ __global__ void ged_kv_kernel(KvParams prm)
     Pair P;
     int status = 0;
     load_pair<S>(prm.pairs, b, sm, P, status);
-    kv_apply<S>(P, sm, prm.x + (long long)b * prm.mat_stride, sm.cost);
+    P.maxdeg = max_degree(sm.bits1, P.R, P.W1, sm.bits2, P.C, P.W2);
     float *dst = prm.cost + (long long)b * prm.mat_stride;
+    kv_apply<S>(P, sm, prm.x + (long long)b * prm.mat_stride, dst, sm.cost);      // the output buffer doubles as Y scratch
+    __syncwarp();
     for (int e = lane; e < P.R * P.C; e += 32) dst[e] = sm.cost[e];
 }
 

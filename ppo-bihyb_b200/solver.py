@@ -113,7 +113,7 @@ def solve_batch(pairs: PairSet, base_idx=None, edit_u=None, edit_v=None, solver:
     res = SolveResult(ged=torch.empty(B, **f32), ged_edited=torch.empty(B, **f32),
                       rowmatch=torch.empty(B, m1, **i32), colmatch=torch.empty(B, m2, **i32),
                       iters=torch.empty(B, **i32), status=torch.empty(B, **i32))
-    workspace = torch.empty(B * ms, **f32) if solver == "ipfp" else None
+    workspace = torch.empty(2 * B * ms, **f32) if solver == "ipfp" else None
     if x_init is not None:
         x_init = x_init.to(**f32).contiguous()
         assert x_init.numel() == B * ms, "x_init must be [B, mat_stride]"
