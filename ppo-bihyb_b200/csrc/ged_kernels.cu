@@ -250,6 +250,13 @@ struct LapSlots {
             LapSlots<S, I + 1>::min_value(lm, spc, live);
         }
     }
+    static __device__ __forceinline__ void min_value2(double &lmA, double &lmB, const double (&spc)[2 * S], unsigned live)
+    {
+        if constexpr (I < 2 * S) {
+            lap_min_value<(1u << I)>((I & 1) ? lmB : lmA, spc[I], live);
+            LapSlots<S, I + 1>::min_value2(lmA, lmB, spc, live);
+        }
+    }
     static __device__ __forceinline__ void min_key(unsigned &lk, const double (&spc)[2 * S], double minVal, unsigned live,
                                                    const int (&posk)[2 * S], const int (&kx)[2 * S])
     {
@@ -309,21 +316,30 @@ __device__ int lsape_warp(const float *cost, int n1, int n2, const Slice &sm, un
             asm volatile("" : "+r"(kx[s]));          // keep it in a register (no re-derivation inside the scan loop)
         }
         unsigned live = exist;               // columns still in `remaining`
-        double minVal = 0.0;
+        double minVal = 0.0, rzmin = INFINITY;
         int i = cur, lastk = N << 17;
         unsigned mk;
         int nsteps = 0;
+        bool infeasible = false;
+
+        // operands of the row about to be scanned; loaded one step ahead (right after the winner is known) so that the
+        // shared-memory latency overlaps the bookkeeping of the previous step
+        double ui = u[i];
+        float cs[S], cx;                     // cs: the row's real entries (real rows only); cx: its deletion / insertion entry
+        {
+            const bool real = i < n1;
+            cx = cost[real ? (i * C + n2) : (n1 * C + (i - n1))];
+#pragma unroll
+            for (int s = 0; s < S; ++s) cs[s] = real ? cost[i * C + lane + 32 * s] : 0.0f;
+        }
 
         for (;;) {
             ++nsteps;
-            const double ui = u[i];
             int improved = 0;
             if (i < n1) {                    // real row: n2 substitution entries + its own deletion entry
-                const float *crow = cost + i * C;
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
-                    const double c = (double)crow[lane + 32 * s];
-                    const double r = __dsub_rn(__dsub_rn(__dadd_rn(minVal, c), ui), v[s]);
+                    const double r = __dsub_rn(__dsub_rn(__dadd_rn(minVal, (double)cs[s]), ui), v[s]);
                     if (s == 0) lap_relax<1u>(spc[0], pth[0], improved, r, i, live);
                     if (s == 1) lap_relax<2u>(spc[s], pth[s], improved, r, i, live);
                     if (s == 2) lap_relax<4u>(spc[s], pth[s], improved, r, i, live);
@@ -332,51 +348,66 @@ __device__ int lsape_warp(const float *cost, int n1, int n2, const Slice &sm, un
                     if (s == 5) lap_relax<32u>(spc[s], pth[s], improved, r, i, live);
                     if (s == 6) lap_relax<64u>(spc[s], pth[s], improved, r, i, live);
                 }
-                const double rd = __dsub_rn(__dadd_rn(minVal, (double)crow[n2]), ui);
+                const double rd = __dsub_rn(__dadd_rn(minVal, (double)cx), ui);
                 const unsigned hl = (lane == (i & 31)) ? (live & ((1u << S) << (i >> 5))) : 0u;
                 LapSlots<S>::relax_range(spc, pth, improved, v, rd, i, hl, S, 2 * S);
             } else {                         // insertion row of column a0: its own entry + the zero block
                 const int a0 = i - n1;
-                const double ra = __dsub_rn(__dadd_rn(minVal, (double)cost[n1 * C + a0]), ui);
+                const double ra = __dsub_rn(__dadd_rn(minVal, (double)cx), ui);
                 const unsigned hl = (lane == (a0 & 31)) ? (live & (1u << (a0 >> 5))) : 0u;
                 LapSlots<S>::relax_range(spc, pth, improved, v, ra, i, hl, 0, S);
+                // zero block: r = rz - v[j].  Rounding is monotone in rz, and after a scan with value rz0 every remaining
+                // deletion column has spc <= fl(rz0 - v[j]); a later insertion row with rz >= rz0 cannot lower any of them.
                 const double rz = __dsub_rn(__dadd_rn(minVal, 0.0), ui);
-                LapSlots<S>::relax_range(spc, pth, improved, v, rz, i, live, S, 2 * S);
+                if (rz < rzmin) {
+                    rzmin = rz;
+                    LapSlots<S>::relax_range(spc, pth, improved, v, rz, i, live, S, 2 * S);
+                }
             }
 
-            // If no shortest-path cost changed, the minimum over the remaining columns is still minVal as long as one
-            // of them attains it: go straight to the tie-break (pass 2); otherwise recompute the minimum (pass 1).
+            // Tie-break among the columns that still attain minVal (pass 2).  If some shortest-path cost was lowered
+            // (a lane then bids key 0, below every real key) or no remaining column attains minVal (all bids are ~0u),
+            // the minimum has to be recomputed first (pass 1).
             unsigned lk = 0xffffffffu;
-            bool need_min = __any_sync(kFull, improved != 0);
-            if (!need_min) {
-                LapSlots<S>::min_key(lk, spc, minVal, live, posk, kx);
-                mk = __reduce_min_sync(kFull, lk);
-                need_min = (mk == 0xffffffffu);
-            }
-            if (need_min) {
-                double lm = INFINITY;
-                LapSlots<S>::min_value(lm, spc, live);
+            LapSlots<S>::min_key(lk, spc, minVal, live, posk, kx);
+            lk = improved ? 0u : lk;
+            mk = __reduce_min_sync(kFull, lk);
+            if (mk - 1u >= 0xfffffffeu) {
+                double lmA = INFINITY, lmB = INFINITY;          // two independent chains
+                LapSlots<S>::min_value2(lmA, lmB, spc, live);
+                const double lm = (lmB < lmA) ? lmB : lmA;
                 unsigned ohi, olo;
                 ord_from_double(lm, ohi, olo);
                 const unsigned mhi = __reduce_min_sync(kFull, ohi);
                 const unsigned mlo = __reduce_min_sync(kFull, ohi == mhi ? olo : 0xffffffffu);
                 minVal = double_from_ord(mhi, mlo);
-                if (minVal == INFINITY) return GED_ST_INFEASIBLE;
                 lk = 0xffffffffu;
                 LapSlots<S>::min_key(lk, spc, minVal, live, posk, kx);
                 mk = __reduce_min_sync(kFull, lk);
+                const bool inf = (minVal == INFINITY);          // nothing reachable: leave the loop, report after it
+                infeasible |= inf;
+                mk = inf ? 0u : mk;
             }
 
+            const int r4star = (int)(mk & 511u) - 1;
+            {   // operands of the next row
+                const int in = max(r4star, 0);
+                const bool real = in < n1;
+                ui = u[in];
+                cx = cost[real ? (in * C + n2) : (n1 * C + (in - n1))];
+#pragma unroll
+                for (int s = 0; s < S; ++s) if (real) cs[s] = cost[in * C + lane + 32 * s];
+            }
             // the winning column leaves `remaining`; the column at its end takes the freed position
             lastk -= 1 << 17;
             const int posstark = (int)((mk & 0xfffe0000u) ^ ((mk & (512u << 17)) ? (512u << 17) : (511u << 17)));
             if (lk == mk) live &= ~(1u << ((mk >> 14) & 7u));
 #pragma unroll
             for (int s = 0; s < 2 * S; ++s) posk[s] = (posk[s] == lastk) ? posstark : posk[s];
-            const int r4star = (int)(mk & 511u) - 1;
             if (r4star < 0) break;
             i = r4star;
         }
+        if (infeasible) return GED_ST_INFEASIBLE;
         steps += nsteps;
         const int wl = (int)((mk >> 9) & 31u), ws = (int)((mk >> 14) & 7u);
         const int sink = (ws < S) ? (wl + 32 * ws) : (n2 + wl + 32 * (ws - S));
@@ -815,6 +846,10 @@ __global__ void ged_solve_kernel(SolveParams prm)
     unsigned long long lap_steps = 0;
     int iters = 0;
     double best_ub = INFINITY;
+#ifdef GED_TIMING
+    long long t_lap = 0, t_kv = 0;
+    const long long t_begin = clock64();
+#endif
 
     if (status == 0) {
         if (prm.x_init) {
@@ -850,13 +885,25 @@ __global__ void ged_solve_kernel(SolveParams prm)
     if (status == 0 && prm.solver_kind == GED_SOLVER_IPFP) {
         for (int it = 0; it < prm.max_iter; ++it) {
             iters = it + 1;
+#ifdef GED_TIMING
+            const long long tk0 = clock64();
+#endif
             kv_apply<S>(P, sm, X, Y, sm.cost);                           // ged_env.py:269
+#ifdef GED_TIMING
+            t_kv += clock64() - tk0;
+#endif
             const double s_vv = dot_flat(sm.cost, X, RC);                // = last_v^T K last_v, ged_env.py:283
             if (out.tr_cost) {
                 float *dst = out.tr_cost + ((long long)b * prm.max_iter + it) * prm.mat_stride;
                 for (int e = lane; e < RC; e += 32) dst[e] = sm.cost[e];
             }
+#ifdef GED_TIMING
+            const long long tl0 = clock64();
+#endif
             status |= lsape_warp<S>(sm.cost, n1, n2, sm, &lap_steps);   // ged_env.py:270
+#ifdef GED_TIMING
+            t_lap += clock64() - tl0;
+#endif
             if (status != 0) break;
             const double ub = score_assignment(P, sm, nnz1, nnz2, sm.rowmatch, sm.colmatch);   // :271
             if (ub < best_ub) {                                          // :272-274
@@ -919,6 +966,11 @@ __global__ void ged_solve_kernel(SolveParams prm)
             ged_base = (float)score_assignment(P, sm, nnz1 + (was_present ? 2 : -2), nnz2, sm.bestrow, sm.bestcol);
         }
     }
+#ifdef GED_TIMING
+    if (lane == 0) printf("solve %d: total %lld cycles, lap %lld (%.1f%%), kv %lld (%.1f%%), lap steps %llu -> %.1f cycles/step\n", b,
+                          clock64() - t_begin, t_lap, 100.0 * t_lap / (clock64() - t_begin), t_kv, 100.0 * t_kv / (clock64() - t_begin),
+                          lap_steps, (double)t_lap / (double)lap_steps);
+#endif
     if (lane == 0) {
         out.ged[b] = ged_base;
         if (out.ged_edited) out.ged_edited[b] = ged_edit;
