@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GED_ABI_VERSION 2
+#define GED_ABI_VERSION 3
 
 /* call-level errors */
 #define GED_OK 0
@@ -106,7 +106,8 @@ typedef struct ged_solve_out {
 } ged_solve_out;
 
 /* Replaces GEDenv.step / solve_feasible_ged / ipfp_ged / hungarian_ged for a whole candidate batch
- * (utils/ged_env.py:110-158, 256-289, 303-326).  One warp per candidate, pair state in shared memory. */
+ * (utils/ged_env.py:110-158, 256-289, 303-326).  One warp per candidate; the LAP's cost matrix lives in tensor memory
+ * (tcgen05.ld/st) for four warps of every CTA and in shared memory for the others. */
 int ged_solve_batch(const ged_solve_desc *desc, const ged_solve_out *out, void *stream);
 
 /* Replaces hungarian_lap (utils/ged_env.py:329-351) incl. scipy's linear_sum_assignment with its exact traversal
@@ -117,8 +118,9 @@ int ged_lsape_batch(int32_t B, const int32_t *n1, const int32_t *n2, int32_t max
                     int32_t *rowmatch, int32_t match_stride_1, int32_t *colmatch, int32_t match_stride_2,
                     float *lb, int32_t *status, void *stream);
 
-/* Replaces torch.mm(k, v) of ipfp_ged (utils/ged_env.py:269) without K: cost_b = K_b vec(X_b) from the factors. */
-int ged_kv_batch(const ged_pairs *pairs, const float *x, float *cost, int64_t mat_stride, void *stream);
+/* Replaces torch.mm(k, v) of ipfp_ged (utils/ged_env.py:269) without K: cost_b = K_b vec(X_b) from the factors.
+ * x, cost and scratch hold one R x C matrix per pair at b * mat_stride; scratch receives X * A2^T. */
+int ged_kv_batch(const ged_pairs *pairs, const float *x, float *cost, float *scratch, int64_t mat_stride, void *stream);
 
 /* Replaces GEDenv.comp_ged (utils/ged_env.py:245-253) for binary x given as assignments: the coalesced edit-cost
  * reduction.  Candidate b scores (rowmatch_b, colmatch_b) on base pair base_idx[b] (identity if NULL). */

@@ -29,8 +29,11 @@
  *       t1 = a<n2 ? rsP[i] - P[i,a] : rsP[i]      rsP[i] = sum_{j in N1(i)} rs[j]   P[i,a] = sum_{j in N1(i)} X[j,a]
  *       t2 = i<n1 ? csQ[a] - Q[i,a] : csQ[a]      csQ[a] = sum_{b in N2(a)} cs[b]   Q[i,a] = sum_{b in N2(a)} X[i,b]
  *       T3 = sum_{j in N1(i)} ( sum_{b in N2(a)} X[j,b] )
- *   Scalars in fp64 with a 32-lane strided partial sum followed by an xor-butterfly (16,8,4,2,1):
- *       s_vv = <cost, X>      over flat e;   s_vb = <cost, b> over t = 0..n1+n2-1 (rows, then inserted columns)
+ *   Scalars in fp64: 32 partial sums followed by an xor-butterfly (16,8,4,2,1) (canonical order v2):
+ *       s_vv = <cost, X>: partial[a & 31] accumulates cost[i,a]*X[i,a] over rows i ascending, then a ascending;
+ *       s_vb = <cost, b>: partial[c & 31] accumulates cost[t, c] for rows t ascending with c = the matched column
+ *              (n2 for a deleted row), then partial[a & 31] accumulates cost[n1, a] for inserted columns a ascending;
+ *       node-cost sums (ub): partial[t & 31] over t = 0..n1+n2-1 (rows, then inserted columns)
  *   alpha = s_vb - s_vv ; beta = (ub - (s_vb + s_vb)) + s_vv ; t0 = -alpha/beta ; t0f = (float)t0
  *   if (beta <= 0 || t0f >= 1) X = b else X[e] = X[e] + t0f*(b[e] - X[e])   (fp32 sub, mul, add; no fma)
  *   break if |s_vv - s_vb| / s_vv < 1e-3   (fp64; NaN compares false)
@@ -325,11 +328,24 @@ static double lane_butterfly(double *p)
     return p[0];
 }
 
-static double dot_flat(const float *a, const float *b, int n)
+/* <cost, X> in the canonical order: partial[a & 31], rows ascending then columns ascending */
+static double dot_rows(const float *a, const float *b, int R, int C)
 {
     double p[32];
     for (int l = 0; l < 32; ++l) p[l] = 0.0;
-    for (int e = 0; e < n; ++e) p[e & 31] = p[e & 31] + (double)a[e] * (double)b[e];
+    for (int i = 0; i < R; ++i)
+        for (int c = 0; c < C; ++c) p[c & 31] = p[c & 31] + (double)a[i * C + c] * (double)b[i * C + c];
+    return lane_butterfly(p);
+}
+
+/* <cost, b> for a binary b in the canonical order: partial index = matched column & 31 */
+static double matched_sum_cols(int n1, int n2, const float *M, const int32_t *rowmatch, const int32_t *colmatch)
+{
+    const int C = n2 + 1;
+    double p[32];
+    for (int l = 0; l < 32; ++l) p[l] = 0.0;
+    for (int t = 0; t < n1; ++t) { const int c = rowmatch[t]; p[c & 31] = p[c & 31] + (double)M[t * C + c]; }
+    for (int a = 0; a < n2; ++a) if (colmatch[a] == n1) p[a & 31] = p[a & 31] + (double)M[n1 * C + a];
     return lane_butterfly(p);
 }
 
@@ -453,13 +469,13 @@ int ged_oracle_solve(int n1, int n2, const uint8_t *adj1, const uint8_t *adj2, c
         for (int it = 0; it < max_iter; ++it) {
             iters = it + 1;
             kv_apply(&k, Cn, X, cost);
-            double s_vv = dot_flat(cost, X, RC);
+            double s_vv = dot_rows(cost, X, R, C);
             st = ged_oracle_lsape(n1, n2, cost, rm, cm, NULL, &steps);
             total_steps += steps;
             if (st != GED_OK) goto done;
             double ub = score_assignment(n1, n2, a1, a2, Cn, rm, cm);
             if (ub < best_ub) { best_ub = ub; memcpy(brm, rm, sizeof(int32_t) * n1); memcpy(bcm, cm, sizeof(int32_t) * n2); }
-            double s_vb = matched_sum(n1, n2, cost, rm, cm);
+            double s_vb = matched_sum_cols(n1, n2, cost, rm, cm);
             double alpha = s_vb - s_vv;
             double beta = (ub - (s_vb + s_vb)) + s_vv;
             double t0 = -alpha / beta;
@@ -494,4 +510,4 @@ done:
     return st;
 }
 
-const char *ged_oracle_version(void) { return "ged_oracle 1 (canonical order v1)"; }
+const char *ged_oracle_version(void) { return "ged_oracle 2 (canonical order v2)"; }

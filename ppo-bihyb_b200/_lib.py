@@ -19,7 +19,7 @@ c_u64p = ctypes.POINTER(ctypes.c_ulonglong)
 GED_OK, GED_E_BADARG, GED_E_TOO_LARGE, GED_E_CUDA = 0, 1, 2, 3
 GED_ST_INVALID_COST, GED_ST_INFEASIBLE, GED_ST_BAD_GRAPH = 1, 2, 4
 GED_SOLVER_IPFP, GED_SOLVER_HUNGARIAN = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # every symbol include/ged_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED_SYMBOLS = (
@@ -96,7 +96,7 @@ def load():
                                     ctypes.c_int64, c_i32p, ctypes.c_int32, c_i32p, ctypes.c_int32, c_f32p, c_i32p,
                                     ctypes.c_void_p]
     lib.ged_lsape_batch.restype = ctypes.c_int
-    lib.ged_kv_batch.argtypes = [ctypes.POINTER(GedPairs), c_f32p, c_f32p, ctypes.c_int64, ctypes.c_void_p]
+    lib.ged_kv_batch.argtypes = [ctypes.POINTER(GedPairs), c_f32p, c_f32p, c_f32p, ctypes.c_int64, ctypes.c_void_p]
     lib.ged_kv_batch.restype = ctypes.c_int
     lib.ged_score_batch.argtypes = [ctypes.POINTER(GedPairs), ctypes.c_int32, c_i32p, c_i32p, ctypes.c_int32,
                                     c_i32p, ctypes.c_int32, c_f32p, ctypes.c_void_p]

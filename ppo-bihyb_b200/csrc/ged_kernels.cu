@@ -4,16 +4,23 @@
 // [construct_k :160-228, never materialised] -> ipfp_ged :256-289 -> hungarian_ged :303-326 ->
 // hungarian_lap :329-351 -> scipy linear_sum_assignment :407 -> comp_ged :245-253.
 //
-// Execution model: ONE WARP PER CANDIDATE SOLVE.  The sequential core of the path is the LAP projection
-// (a shortest-augmenting-path search whose scan order and tie-breaks must equal SciPy's), so each candidate is
-// owned by a single warp that keeps the LAP's per-column state (dual v, shortest-path cost, position in SciPy's
-// `remaining` vector, predecessor) in REGISTERS, one column per (lane, slot), the cost matrix and row duals in its
-// private slice of shared memory, and the fractional IPFP iterate X in global memory (it is only touched between
-// LAPs and stays L2 resident).  K is never built: K vec(X) is evaluated from the two bit-packed adjacency factors.
-// No __syncthreads anywhere -- warps of a CTA are independent, so a CTA is just a packing unit for occupancy.
+// Execution model: ONE WARP PER CANDIDATE SOLVE.  The sequential core of the path is the LAP projection (a shortest-
+// augmenting-path search whose scan order and tie-breaks must equal SciPy's: ~2000 dependent scan steps per LAP at n=60,
+// 101 LAPs per solve), so a candidate is owned by a single warp that keeps the LAP's per-column state (dual v, shortest-
+// path cost, position in SciPy's `remaining` vector, predecessor) in REGISTERS, one column per (lane, slot).  Throughput
+// is bounded by how many solves are in flight per SM (dependent-latency bound) and, at small sizes, by instruction
+// issue; both are set by where the n1 x n2 cost matrix of the running LAP lives:
+//   * SmemCost: in the warp's private slice of shared memory (15 KB at n=60);
+//   * TmemCost: in TENSOR MEMORY (tcgen05.st / tcgen05.ld, 32x32b shape): TMEM is 128 lanes x 512 columns of 32 bits
+//     per SM, each warp of a CTA owns one 32-lane quarter, element (i, a) sits at lane a & 31, column i * S + (a >> 5);
+//     a row of the matrix is ONE tcgen05.ld.  It is used purely as a second 256 KB scratchpad (no MMA): a hybrid CTA
+//     runs 4 TMEM-backed solves next to k shared-memory-backed ones, roughly doubling the solves in flight per SM.
+// The fractional IPFP iterate X and Y = X A2^T live in global memory (touched only between LAPs, L2 resident).
+// K is never built: K vec(X) is evaluated from the two bit-packed adjacency factors.  Warps never synchronise with each
+// other (the only CTA-wide barriers bracket the TMEM allocation).
 //
-// All floating-point arithmetic follows the canonical order documented in oracle/ged_oracle.c (no FMA
-// contraction: explicit *_rn intrinsics, and the file is compiled with --fmad=false).
+// All floating-point arithmetic follows the canonical order documented in oracle/ged_oracle.c (no FMA contraction:
+// explicit *_rn intrinsics, and the file is compiled with --fmad=false).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -23,32 +30,38 @@
 
 #include "../../include/ged_b200.h"
 
-namespace {
+// The file is compiled several times (ppo-bihyb_b200/build.py, in parallel): once per slot count S with -DGED_TU_S=S, each
+// of those translation units providing the kernels of that S behind three plain functions (launch_solve_sS, ...), and once
+// without the macro for the size-independent kernels, the dispatch and the C-ABI.
+namespace ged_impl {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMaxS = 7;                       // slots per column group: graphs up to 32*7 = 224 nodes
 constexpr int kMaxSmemBytes = 227 * 1024;
+constexpr int kMaxDeg = 6;                     // neighbour lists held in registers up to this degree (molecules: <= 5)
+constexpr int kTmemWarps = 4;                  // one warp per 32-lane quarter of tensor memory
 
-thread_local char g_err[512] = "";
+extern thread_local char g_err[512];     // defined in the main translation unit
 
-int fail(int code, const char *msg)
+static int fail(int code, const char *msg)
 {
     snprintf(g_err, sizeof(g_err), "%s", msg);
     return code;
 }
-int fail_cuda(cudaError_t e, const char *where)
+static int fail_cuda(cudaError_t e, const char *where)
 {
     snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
     return GED_E_CUDA;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Shared-memory slice of one warp (host and device agree through this one function).
+// Shared-memory slice of one warp (host and device agree through this one function).  `bytes` is the slice without
+// the cost matrix, `cost_bytes` the n1 x n2 block a shared-memory-backed solve adds.
 // ---------------------------------------------------------------------------------------------------------------
 struct SliceLayout {
-    int off_u, off_cost, off_bits1, off_bits2, off_rs, off_rsP, off_cs, off_csQ, off_lab1, off_lab2;
+    int off_u, off_cdel, off_cins, off_rowbuf, off_bits1, off_bits2, off_lab1, off_lab2;
     int off_row4col, off_col4row, off_path, off_rowmatch, off_colmatch, off_bestrow, off_bestcol;
-    int bytes;
+    int bytes, cost_bytes;
 };
 
 __host__ __device__ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
@@ -60,14 +73,12 @@ __host__ __device__ inline SliceLayout make_layout(int max_n1, int max_n2)
     const int W2 = (max_n2 + 31) / 32 > 0 ? (max_n2 + 31) / 32 : 1;
     SliceLayout L;
     int o = 0;
-    L.off_u = o;        o += 8 * Nm;
-    L.off_cost = o;     o += 4 * (Rm * Cm + 32 * ((Cm + 31) / 32));   // + one padded row: lanes read past C
+    L.off_u = o;        o += 8 * (Nm + 2);     // LAP row duals (fp64); K*X temporaries rs, rsP, cs alias it
+    L.off_cdel = o;     o += 4 * Rm;           // cost[i][n2]: deletion cost of row i
+    L.off_cins = o;     o += 4 * Cm;           // cost[n1][a]: insertion cost of column a
+    L.off_rowbuf = o;   o += 2 * 4 * align_up(Cm, 4);   // two rows of X (double buffered) for the Y = X A2^T gathers
     L.off_bits1 = o;    o += 4 * Rm * W1;
     L.off_bits2 = o;    o += 4 * Cm * W2;
-    L.off_rs = o;       o += 4 * Rm;
-    L.off_rsP = o;      o += 4 * Rm;
-    L.off_cs = o;       o += 4 * Cm;
-    L.off_csQ = o;      o += 4 * Cm;
     L.off_lab1 = o;     o += 4 * Rm;
     L.off_lab2 = o;     o += 4 * Cm;
     L.off_row4col = o;  o += 2 * Nm;
@@ -78,29 +89,32 @@ __host__ __device__ inline SliceLayout make_layout(int max_n1, int max_n2)
     L.off_bestrow = o;  o += 2 * Rm;
     L.off_bestcol = o;  o += 2 * Cm;
     L.bytes = align_up(o, 16);
+    L.cost_bytes = align_up(4 * (max_n1 * max_n2 + 32 * ((max_n2 + 31) / 32 + 1)), 16);   // + padding: lanes read past n2
     return L;
 }
 
 struct Slice {
     double *u;
-    float *cost;
+    float *rs, *rsP, *cs;                    // alias u (live only inside kv_apply / init_cost)
+    float *cdel, *cins, *rowbuf;
     uint32_t *bits1, *bits2;
-    float *rs, *rsP, *cs, *csQ;
     int32_t *lab1, *lab2;
     int16_t *row4col, *col4row, *path, *rowmatch, *colmatch, *bestrow, *bestcol;
+    float *cost;                             // shared-memory cost block (SmemCost only), nullptr otherwise
 };
 
-__device__ inline Slice carve(unsigned char *base, const SliceLayout &L)
+__device__ inline Slice carve(unsigned char *base, const SliceLayout &L, int max_n1, int max_n2, bool with_cost)
 {
     Slice s;
     s.u = reinterpret_cast<double *>(base + L.off_u);
-    s.cost = reinterpret_cast<float *>(base + L.off_cost);
+    s.rs = reinterpret_cast<float *>(base + L.off_u);
+    s.rsP = s.rs + (max_n1 + 1);
+    s.cs = s.rsP + (max_n1 + 1);
+    s.cdel = reinterpret_cast<float *>(base + L.off_cdel);
+    s.cins = reinterpret_cast<float *>(base + L.off_cins);
+    s.rowbuf = reinterpret_cast<float *>(base + L.off_rowbuf);
     s.bits1 = reinterpret_cast<uint32_t *>(base + L.off_bits1);
     s.bits2 = reinterpret_cast<uint32_t *>(base + L.off_bits2);
-    s.rs = reinterpret_cast<float *>(base + L.off_rs);
-    s.rsP = reinterpret_cast<float *>(base + L.off_rsP);
-    s.cs = reinterpret_cast<float *>(base + L.off_cs);
-    s.csQ = reinterpret_cast<float *>(base + L.off_csQ);
     s.lab1 = reinterpret_cast<int32_t *>(base + L.off_lab1);
     s.lab2 = reinterpret_cast<int32_t *>(base + L.off_lab2);
     s.row4col = reinterpret_cast<int16_t *>(base + L.off_row4col);
@@ -110,6 +124,7 @@ __device__ inline Slice carve(unsigned char *base, const SliceLayout &L)
     s.colmatch = reinterpret_cast<int16_t *>(base + L.off_colmatch);
     s.bestrow = reinterpret_cast<int16_t *>(base + L.off_bestrow);
     s.bestcol = reinterpret_cast<int16_t *>(base + L.off_bestcol);
+    s.cost = with_cost ? reinterpret_cast<float *>(base + L.bytes) : nullptr;
     return s;
 }
 
@@ -118,6 +133,65 @@ struct Pair {
     int n1, n2, R, C, N, W1, W2;
     int maxdeg;                 // max node degree over both graphs (after the candidate edit)
     const float *node_cost;     // global, R x C, or nullptr -> label metric
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Where the n1 x n2 block of the LAP's cost matrix lives.  Element (i, a) belongs to lane a & 31, slot a >> 5.
+//   put(i, s, v)   : every lane stores its element (i, lane + 32 s)   (lanes past n2 store a don't-care value)
+//   row(i, cs)     : every lane fetches its S elements of row i
+//   flush()        : stores are visible to later row() calls of this warp
+// ---------------------------------------------------------------------------------------------------------------
+template <int S>
+struct SmemCost {
+    static constexpr bool kPrefetch = true;  // row() is a plain LDS: issue it a step ahead, the scoreboard does the rest
+    float *base;
+    int stride;                              // = n2
+    __device__ __forceinline__ void put(int i, int s, float v) const
+    {
+        const int a = (threadIdx.x & 31) + 32 * s;
+        if (a < stride) base[i * stride + a] = v;
+    }
+    __device__ __forceinline__ void row(int i, float (&cs)[S]) const
+    {
+        const float *p = base + i * stride + (threadIdx.x & 31);
+#pragma unroll
+        for (int s = 0; s < S; ++s) cs[s] = p[32 * s];
+    }
+    __device__ __forceinline__ void flush() const { __syncwarp(); }
+};
+
+template <int S>
+struct TmemCost {
+    static constexpr bool kPrefetch = false; // tcgen05.ld + wait::ld is ~12 cycles: fetched where it is consumed
+    uint32_t taddr;                          // (first lane of this warp's quarter) << 16 | first column
+    __device__ __forceinline__ void put(int i, int s, float v) const
+    {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr + (uint32_t)(i * S + s)), "r"(__float_as_uint(v)) : "memory");
+    }
+    __device__ __forceinline__ void row(int i, float (&cs)[S]) const
+    {
+        const uint32_t a = taddr + (uint32_t)(i * S);
+        uint32_t r[8];
+        if constexpr (S == 1)
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n\ttcgen05.wait::ld.sync.aligned;" : "=r"(r[0]) : "r"(a) : "memory");
+        else if constexpr (S == 2)
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];\n\ttcgen05.wait::ld.sync.aligned;" : "=r"(r[0]), "=r"(r[1]) : "r"(a) : "memory");
+        else if constexpr (S == 3)
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%3];\n\ttcgen05.ld.sync.aligned.32x32b.x1.b32 {%2}, [%4];\n\t"
+                         "tcgen05.wait::ld.sync.aligned;" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]) : "r"(a), "r"(a + 2u) : "memory");
+        else if constexpr (S == 4)
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n\ttcgen05.wait::ld.sync.aligned;"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a) : "memory");
+        else {
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[s]) : "r"(a + (uint32_t)s) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) cs[s] = __uint_as_float(r[s]);
+    }
+    __device__ __forceinline__ void flush() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -167,15 +241,6 @@ __device__ __forceinline__ bool bit_at(const uint32_t *bits, int W, int i, int j
     return (bits[i * W + (j >> 5)] >> (j & 31)) & 1u;
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// LSAPE through the expanded (n1+n2)^2 LAP, SciPy order (hungarian_lap ged_env.py:329-351; scipy
-// rectangular_lsap augmenting_path + solve).  Columns of the expanded matrix live in registers:
-//   real column a      -> lane a & 31, slot a >> 5            (slots 0 .. S-1)
-//   deletion column k  -> lane k & 31, slot S + (k >> 5)      (expanded column index n2 + k)
-// `pos` is the column's index in SciPy's `remaining` vector (initially N-1-j, swap-removed on selection); the
-// selection rule "last minimum whose column is unassigned, else first minimum" becomes a lexicographic arg-min
-// over (spc, key) with key = unassigned ? -1-pos : pos, done with three integer warp reductions.
-// ---------------------------------------------------------------------------------------------------------------
 // Order-preserving map double -> (hi, lo) unsigned pair (and back), so that a 64-bit floating-point minimum becomes two
 // 32-bit integer warp reductions.  -0.0 cannot occur among the reduced costs (minVal starts at +0.0 and x - x = +0.0 in
 // round-to-nearest), so the map agrees with IEEE comparison on every value it sees.
@@ -235,19 +300,25 @@ __device__ __forceinline__ void lap_min_key(unsigned &lk, double spc, double min
 
 template <int S, int I = 0>
 struct LapSlots {
-    static __device__ __forceinline__ void relax_range(double (&spc)[2 * S], int (&pth)[2 * S], int &improved,
-                                                       const double (&v)[2 * S], double base, int i, unsigned live, int lo, int hi)
+    // slots [LO, HI): relax with r = base - v[slot]
+    template <int LO, int HI>
+    static __device__ __forceinline__ void relax_base(double (&spc)[2 * S], int (&pth)[2 * S], int &improved,
+                                                      const double (&v)[2 * S], double base, int i, unsigned live)
     {
         if constexpr (I < 2 * S) {
-            if (I >= lo && I < hi) lap_relax<(1u << I)>(spc[I], pth[I], improved, __dsub_rn(base, v[I]), i, live);
-            LapSlots<S, I + 1>::relax_range(spc, pth, improved, v, base, i, live, lo, hi);
+            if constexpr (I >= LO && I < HI) lap_relax<(1u << I)>(spc[I], pth[I], improved, __dsub_rn(base, v[I]), i, live);
+            LapSlots<S, I + 1>::template relax_base<LO, HI>(spc, pth, improved, v, base, i, live);
         }
     }
-    static __device__ __forceinline__ void min_value(double &lm, const double (&spc)[2 * S], unsigned live)
+    // real slots [0, S): relax with SciPy's r = ((minVal + c) - u[i]) - v[j]
+    static __device__ __forceinline__ void relax_row(double (&spc)[2 * S], int (&pth)[2 * S], int &improved,
+                                                     const double (&v)[2 * S], const float (&cs)[S], double minVal, double ui,
+                                                     int i, unsigned live)
     {
-        if constexpr (I < 2 * S) {
-            lap_min_value<(1u << I)>(lm, spc[I], live);
-            LapSlots<S, I + 1>::min_value(lm, spc, live);
+        if constexpr (I < S) {
+            const double r = __dsub_rn(__dsub_rn(__dadd_rn(minVal, (double)cs[I]), ui), v[I]);
+            lap_relax<(1u << I)>(spc[I], pth[I], improved, r, i, live);
+            LapSlots<S, I + 1>::relax_row(spc, pth, improved, v, cs, minVal, ui, i, live);
         }
     }
     static __device__ __forceinline__ void min_value2(double &lmA, double &lmB, const double (&spc)[2 * S], unsigned live)
@@ -267,26 +338,23 @@ struct LapSlots {
     }
 };
 
+// ---------------------------------------------------------------------------------------------------------------
 // LSAPE through the expanded (n1+n2)^2 LAP in SciPy's order (hungarian_lap ged_env.py:329-351; scipy rectangular_lsap).
+// The expanded matrix is never formed: its real block comes from the cost store, row i's deletion entry from
+// sm.cdel[i], column a's insertion entry from sm.cins[a], everything else is +inf or 0 by construction.
 // Columns live in registers, one per (lane, slot): real column a -> lane a & 31, slot a >> 5; deletion column n2+k ->
 // lane k & 31, slot S + (k >> 5).  Tie-break key of a column:  kk << 17 | slot << 14 | lane << 9 | (row4col + 1), with
 // kk = pos ^ 511 for an unassigned column (SciPy: the LAST unassigned minimum wins) and pos ^ 512 = 512 + pos for an
 // assigned one (else the FIRST minimum wins); pos = index in SciPy's `remaining` vector.  The smallest key wins.
-template <int S>
-__device__ int lsape_warp(const float *cost, int n1, int n2, const Slice &sm, unsigned long long *steps_out)
+// `invalid` = the producer of the matrix saw NaN / -inf (scipy: RECTANGULAR_LSAP_INVALID).
+// ---------------------------------------------------------------------------------------------------------------
+template <int S, class Store>
+__device__ int lsape_warp(const Store &store, bool invalid, int n1, int n2, const Slice &sm, unsigned long long *steps_out)
 {
     const int lane = threadIdx.x & 31;
-    const int N = n1 + n2, C = n2 + 1;
+    const int N = n1 + n2;
     double *u = sm.u;
-
-    {   // scipy rejects NaN / -inf (RECTANGULAR_LSAP_INVALID); the dummy-dummy entry is not part of the LAP
-        bool bad = false;
-        for (int e = lane; e < (n1 + 1) * C - 1; e += 32) {
-            const float c = cost[e];
-            bad |= (c != c) || (c == -INFINITY);
-        }
-        if (__any_sync(kFull, bad)) return GED_ST_INVALID_COST;
-    }
+    if (invalid) return GED_ST_INVALID_COST;
 
     double v[2 * S];
     unsigned exist = 0;                      // bit s set: this lane's slot s holds a column of the expanded matrix
@@ -322,57 +390,50 @@ __device__ int lsape_warp(const float *cost, int n1, int n2, const Slice &sm, un
         int nsteps = 0;
         bool infeasible = false;
 
-        // operands of the row about to be scanned; loaded one step ahead (right after the winner is known) so that the
-        // shared-memory latency overlaps the bookkeeping of the previous step
+        // operands of the row about to be scanned: row dual, the row's deletion / insertion entry and (shared-memory store)
+        // its real entries are loaded one step ahead, right after the winner is known, so that the latency overlaps the
+        // bookkeeping of the previous step
+        bool real = i < n1;
         double ui = u[i];
-        float cs[S], cx;                     // cs: the row's real entries (real rows only); cx: its deletion / insertion entry
-        {
-            const bool real = i < n1;
-            cx = cost[real ? (i * C + n2) : (n1 * C + (i - n1))];
+        float cx = real ? sm.cdel[i] : sm.cins[i - n1];
+        float cs[S];
 #pragma unroll
-            for (int s = 0; s < S; ++s) cs[s] = real ? cost[i * C + lane + 32 * s] : 0.0f;
-        }
+        for (int s = 0; s < S; ++s) cs[s] = 0.0f;
+        if (Store::kPrefetch && real) store.row(i, cs);
 
         for (;;) {
             ++nsteps;
             int improved = 0;
-            if (i < n1) {                    // real row: n2 substitution entries + its own deletion entry
-#pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    const double r = __dsub_rn(__dsub_rn(__dadd_rn(minVal, (double)cs[s]), ui), v[s]);
-                    if (s == 0) lap_relax<1u>(spc[0], pth[0], improved, r, i, live);
-                    if (s == 1) lap_relax<2u>(spc[s], pth[s], improved, r, i, live);
-                    if (s == 2) lap_relax<4u>(spc[s], pth[s], improved, r, i, live);
-                    if (s == 3) lap_relax<8u>(spc[s], pth[s], improved, r, i, live);
-                    if (s == 4) lap_relax<16u>(spc[s], pth[s], improved, r, i, live);
-                    if (s == 5) lap_relax<32u>(spc[s], pth[s], improved, r, i, live);
-                    if (s == 6) lap_relax<64u>(spc[s], pth[s], improved, r, i, live);
-                }
+            unsigned lk = 0xffffffffu;
+            bool need_min = true;
+            if (real) {                      // real row: n2 substitution entries + its own deletion entry
+                if (!Store::kPrefetch) store.row(i, cs);
+                LapSlots<S>::relax_row(spc, pth, improved, v, cs, minVal, ui, i, live);
                 const double rd = __dsub_rn(__dadd_rn(minVal, (double)cx), ui);
                 const unsigned hl = (lane == (i & 31)) ? (live & ((1u << S) << (i >> 5))) : 0u;
-                LapSlots<S>::relax_range(spc, pth, improved, v, rd, i, hl, S, 2 * S);
+                LapSlots<S>::template relax_base<S, 2 * S>(spc, pth, improved, v, rd, i, hl);
+                // a real row almost always lowers something: recompute the minimum right away
             } else {                         // insertion row of column a0: its own entry + the zero block
                 const int a0 = i - n1;
                 const double ra = __dsub_rn(__dadd_rn(minVal, (double)cx), ui);
                 const unsigned hl = (lane == (a0 & 31)) ? (live & (1u << (a0 >> 5))) : 0u;
-                LapSlots<S>::relax_range(spc, pth, improved, v, ra, i, hl, 0, S);
+                LapSlots<S>::template relax_base<0, S>(spc, pth, improved, v, ra, i, hl);
                 // zero block: r = rz - v[j].  Rounding is monotone in rz, and after a scan with value rz0 every remaining
                 // deletion column has spc <= fl(rz0 - v[j]); a later insertion row with rz >= rz0 cannot lower any of them.
                 const double rz = __dsub_rn(__dadd_rn(minVal, 0.0), ui);
                 if (rz < rzmin) {
                     rzmin = rz;
-                    LapSlots<S>::relax_range(spc, pth, improved, v, rz, i, live, S, 2 * S);
+                    LapSlots<S>::template relax_base<S, 2 * S>(spc, pth, improved, v, rz, i, live);
                 }
+                // Tie-break among the columns that still attain minVal.  If some shortest-path cost was lowered (that lane
+                // bids key 0, below every real key) or no remaining column attains minVal (all bids are ~0u), the minimum
+                // has to be recomputed first.
+                LapSlots<S>::min_key(lk, spc, minVal, live, posk, kx);
+                lk = improved ? 0u : lk;
+                mk = __reduce_min_sync(kFull, lk);
+                need_min = (mk - 1u >= 0xfffffffeu);
             }
-
-            // Tie-break among the columns that still attain minVal (pass 2).  If some shortest-path cost was lowered
-            // (a lane then bids key 0, below every real key) or no remaining column attains minVal (all bids are ~0u),
-            // the minimum has to be recomputed first (pass 1).
-            unsigned lk = 0xffffffffu;
-            LapSlots<S>::min_key(lk, spc, minVal, live, posk, kx);
-            lk = improved ? 0u : lk;
-            mk = __reduce_min_sync(kFull, lk);
-            if (mk - 1u >= 0xfffffffeu) {
+            if (need_min) {
                 double lmA = INFINITY, lmB = INFINITY;          // two independent chains
                 LapSlots<S>::min_value2(lmA, lmB, spc, live);
                 const double lm = (lmB < lmA) ? lmB : lmA;
@@ -392,11 +453,10 @@ __device__ int lsape_warp(const float *cost, int n1, int n2, const Slice &sm, un
             const int r4star = (int)(mk & 511u) - 1;
             {   // operands of the next row
                 const int in = max(r4star, 0);
-                const bool real = in < n1;
+                real = in < n1;
                 ui = u[in];
-                cx = cost[real ? (in * C + n2) : (n1 * C + (in - n1))];
-#pragma unroll
-                for (int s = 0; s < S; ++s) if (real) cs[s] = cost[in * C + lane + 32 * s];
+                cx = real ? sm.cdel[in] : sm.cins[in - n1];
+                if (Store::kPrefetch && real) store.row(in, cs);
             }
             // the winning column leaves `remaining`; the column at its end takes the freed position
             lastk -= 1 << 17;
@@ -450,234 +510,43 @@ __device__ int lsape_warp(const float *cost, int n1, int n2, const Slice &sm, un
     return GED_ST_OK;
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// cost = K vec(X) from the factors (replaces torch.mm(k, v), ged_env.py:269).  X in global memory, cost in smem.
-//   K vec(X) = A1 X M2^T + M1 X A2^T - 2 A1 X A2^T + Cn o X      (identity checked in the tests)
-// T = number of 32-wide column tiles of a row.
-// ---------------------------------------------------------------------------------------------------------------
-template <int S>
-__device__ void kv_apply_generic(const Pair &P, const Slice &sm, const float *X, float *cost)
-{
-    constexpr int T = S + 1;
-    const int lane = threadIdx.x & 31;
-    const int R = P.R, C = P.C, n1 = P.n1, n2 = P.n2;
-
-    float csacc[T];
-#pragma unroll
-    for (int t = 0; t < T; ++t) csacc[t] = 0.0f;
-    for (int i = 0; i < R; ++i) {
-        float part = 0.0f;
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-            const int a = lane + 32 * t;
-            if (a < C) {
-                const float x = X[i * C + a];
-                csacc[t] = __fadd_rn(csacc[t], x);
-                part = __fadd_rn(part, x);
-            }
-        }
-        part = warp_butterfly(part);
-        if (lane == 0) sm.rs[i] = part;
-    }
-#pragma unroll
-    for (int t = 0; t < T; ++t) { const int a = lane + 32 * t; if (a < C) sm.cs[a] = csacc[t]; }
-    __syncwarp();
-    for (int i = lane; i < R; i += 32) {
-        float s = 0.0f;
-        for (int w = 0; w < P.W1; ++w) {
-            uint32_t word = sm.bits1[i * P.W1 + w];
-            while (word) { const int j = w * 32 + __ffs(word) - 1; word &= word - 1; s = __fadd_rn(s, sm.rs[j]); }
-        }
-        sm.rsP[i] = s;
-    }
-    for (int a = lane; a < C; a += 32) {
-        float s = 0.0f;
-        for (int w = 0; w < P.W2; ++w) {
-            uint32_t word = sm.bits2[a * P.W2 + w];
-            while (word) { const int b = w * 32 + __ffs(word) - 1; word &= word - 1; s = __fadd_rn(s, sm.cs[b]); }
-        }
-        sm.csQ[a] = s;
-    }
-    __syncwarp();
-
-    for (int i = 0; i < R; ++i) {
-        const uint32_t *row1 = sm.bits1 + i * P.W1;
-        const float rsPi = sm.rsP[i];
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-            const int a = lane + 32 * t;
-            if (a < C) {
-                const uint32_t *row2 = sm.bits2 + a * P.W2;
-                float Pv = 0.0f, Qv = 0.0f, T3 = 0.0f;
-                for (int w2 = 0; w2 < P.W2; ++w2) {
-                    uint32_t word2 = row2[w2];
-                    while (word2) { const int b = w2 * 32 + __ffs(word2) - 1; word2 &= word2 - 1; Qv = __fadd_rn(Qv, X[i * C + b]); }
-                }
-                for (int w1 = 0; w1 < P.W1; ++w1) {
-                    uint32_t word1 = row1[w1];
-                    while (word1) {
-                        const int j = w1 * 32 + __ffs(word1) - 1;
-                        word1 &= word1 - 1;
-                        const float *xr = X + j * C;
-                        Pv = __fadd_rn(Pv, xr[a]);
-                        float in = 0.0f;
-                        for (int w2 = 0; w2 < P.W2; ++w2) {
-                            uint32_t word2 = row2[w2];
-                            while (word2) { const int b = w2 * 32 + __ffs(word2) - 1; word2 &= word2 - 1; in = __fadd_rn(in, xr[b]); }
-                        }
-                        T3 = __fadd_rn(T3, in);
-                    }
-                }
-                const float t1 = (a < n2) ? __fsub_rn(rsPi, Pv) : rsPi;
-                const float t2 = (i < n1) ? __fsub_rn(sm.csQ[a], Qv) : sm.csQ[a];
-                float s = __fadd_rn(t1, t2);
-                s = __fsub_rn(s, __fadd_rn(T3, T3));
-                const float d = __fmul_rn(node_cost_at(P, sm, i, a), X[i * C + a]);
-                cost[i * C + a] = __fadd_rn(s, d);
-            }
-        }
-    }
-    __syncwarp();
-}
-
-// Fast path of K vec(X) for graphs whose maximum degree is <= kMaxDeg (molecules: <= 4, +1 for a candidate edit).
-// Same arithmetic, same summation order as kv_apply_generic (and oracle/ged_oracle.c), restructured around
-//     Y = X A2^T   (Y[j,a] = sum_{b in N2(a)} X[j,b], ascending b)
-// so that every inner term is a ROW gather:  P[i,a] = sum_{j in N1(i)} X[j,a],  T3[i,a] = sum_{j in N1(i)} Y[j,a],
-// Q[i,a] = Y[i,a].  X is staged once in the (not yet written) cost region of shared memory for the random column
-// gathers of Y; Y goes to global scratch; the final pass reads X and Y rows with coalesced, mutually independent loads
-// (one L2 round trip per row of the result) and writes cost into shared memory.
-constexpr int kMaxDeg = 6;
-
-__device__ __forceinline__ void decode_neighbours(const uint32_t *row, int W, int (&nb)[kMaxDeg])
-{
-    int w = 0;
-    uint32_t word = row[0];
-#pragma unroll
-    for (int k = 0; k < kMaxDeg; ++k) {
-        while (word == 0u && w + 1 < W) word = row[++w];
-        nb[k] = word ? (w * 32 + __ffs(word) - 1) : -1;
-        word &= word - 1u;
-    }
-}
-
-template <int S>
-__device__ void kv_apply(const Pair &P, const Slice &sm, const float *X, float *Y, float *cost)
-{
-    if (P.maxdeg > kMaxDeg) { kv_apply_generic<S>(P, sm, X, cost); return; }
-    constexpr int T = S + 1;
-    const int lane = threadIdx.x & 31;
-    const int R = P.R, C = P.C, n1 = P.n1, n2 = P.n2, RC = R * C;
-
-    for (int e = lane; e < RC; e += 32) cost[e] = X[e];          // stage X
-    __syncwarp();
-
-    float csacc[T];
-#pragma unroll
-    for (int t = 0; t < T; ++t) csacc[t] = 0.0f;
-    for (int i = 0; i < R; ++i) {
-        float part = 0.0f;
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-            const int a = lane + 32 * t;
-            if (a < C) {
-                const float x = cost[i * C + a];
-                csacc[t] = __fadd_rn(csacc[t], x);
-                part = __fadd_rn(part, x);
-            }
-        }
-        part = warp_butterfly(part);
-        if (lane == 0) sm.rs[i] = part;
-    }
-#pragma unroll
-    for (int t = 0; t < T; ++t) { const int a = lane + 32 * t; if (a < C) sm.cs[a] = csacc[t]; }
-    __syncwarp();
-    for (int i = lane; i < R; i += 32) {
-        int nb[kMaxDeg];
-        decode_neighbours(sm.bits1 + i * P.W1, P.W1, nb);
-        float s = 0.0f;
-#pragma unroll
-        for (int k = 0; k < kMaxDeg; ++k) if (nb[k] >= 0) s = __fadd_rn(s, sm.rs[nb[k]]);
-        sm.rsP[i] = s;
-    }
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-        if (32 * t >= C) break;
-        const int a = lane + 32 * t;
-        if (a < C) {
-            int nb[kMaxDeg];
-            decode_neighbours(sm.bits2 + a * P.W2, P.W2, nb);
-            float s = 0.0f;
-#pragma unroll
-            for (int k = 0; k < kMaxDeg; ++k) if (nb[k] >= 0) s = __fadd_rn(s, sm.cs[nb[k]]);
-            sm.csQ[a] = s;
-            for (int j = 0; j < R; ++j) {                        // Y[j, a]
-                const float *xr = cost + j * C;
-                float in = 0.0f;
-#pragma unroll
-                for (int k = 0; k < kMaxDeg; ++k) if (nb[k] >= 0) in = __fadd_rn(in, xr[nb[k]]);
-                Y[j * C + a] = in;
-            }
-        }
-    }
-    __syncwarp();
-
-    for (int i = 0; i < R; ++i) {
-        int nb[kMaxDeg];
-        decode_neighbours(sm.bits1 + i * P.W1, P.W1, nb);        // warp-uniform
-        const float rsPi = sm.rsP[i];
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-            if (32 * t >= C) break;
-            const int a = lane + 32 * t;
-            if (a < C) {
-                float xv[kMaxDeg], yv[kMaxDeg];
-#pragma unroll
-                for (int k = 0; k < kMaxDeg; ++k) {              // all loads first: they are independent
-                    xv[k] = 0.0f;
-                    yv[k] = 0.0f;
-                    if (nb[k] >= 0) { xv[k] = X[nb[k] * C + a]; yv[k] = Y[nb[k] * C + a]; }
-                }
-                const float xia = X[i * C + a], Qv = Y[i * C + a];
-                float Pv = 0.0f, T3 = 0.0f;
-#pragma unroll
-                for (int k = 0; k < kMaxDeg; ++k)
-                    if (nb[k] >= 0) { Pv = __fadd_rn(Pv, xv[k]); T3 = __fadd_rn(T3, yv[k]); }
-                const float t1 = (a < n2) ? __fsub_rn(rsPi, Pv) : rsPi;
-                const float t2 = (i < n1) ? __fsub_rn(sm.csQ[a], Qv) : sm.csQ[a];
-                float sres = __fadd_rn(t1, t2);
-                sres = __fsub_rn(sres, __fadd_rn(T3, T3));
-                const float d = __fmul_rn(node_cost_at(P, sm, i, a), xia);
-                cost[i * C + a] = __fadd_rn(sres, d);
-            }
-        }
-    }
-    __syncwarp();
-}
-
-// <A, B> over the flat R*C index, fp64: lane-strided partials + butterfly.
-__device__ inline double dot_flat(const float *a_smem, const float *b_glob, int n)
+// <cost, b> for the binary projection b = (rowmatch, colmatch) in the canonical order (oracle: matched_sum_cols):
+// partial[c & 31] accumulates cost[t, c] over rows t ascending (c = matched column, n2 = deleted), then partial[a & 31]
+// accumulates cost[n1, a] over inserted columns a ascending; fp64, xor butterfly.
+template <int S, class Store>
+__device__ double matched_cost_sum(const Store &store, const Slice &sm, int n1, int n2)
 {
     const int lane = threadIdx.x & 31;
     double acc = 0.0;
-    for (int e = lane; e < n; e += 32) acc = __dadd_rn(acc, __dmul_rn((double)a_smem[e], (double)b_glob[e]));
+    for (int t = 0; t < n1; ++t) {
+        float cs[S];
+        store.row(t, cs);
+        const int c = sm.rowmatch[t];
+        float term = sm.cdel[t];
+#pragma unroll
+        for (int s = 0; s < S; ++s) term = (c < n2 && (c >> 5) == s) ? cs[s] : term;
+        if (lane == (c & 31)) acc = __dadd_rn(acc, (double)term);
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const int a = lane + 32 * s;
+        if (a < n2 && sm.colmatch[a] == n1) acc = __dadd_rn(acc, (double)sm.cins[a]);
+    }
     return warp_butterfly(acc);
 }
 
-// Sum of an R x C matrix (shared or global, or the implicit node-cost matrix when M == nullptr) over the matched
-// entries: t < n1 -> (t, rowmatch[t]);  t >= n1 -> (n1, t - n1) if that column is inserted.
-__device__ inline double matched_sum(const Pair &P, const Slice &sm, const float *M, const int16_t *rowmatch, const int16_t *colmatch)
+// Sum of the node costs of an assignment (ub, scoring): t < n1 -> (t, rowmatch[t]);  t >= n1 -> (n1, t - n1) if that
+// column is inserted; partial[t & 31], fp64, xor butterfly (oracle: matched_sum).
+__device__ inline double matched_node_cost(const Pair &P, const Slice &sm, const int16_t *rowmatch, const int16_t *colmatch)
 {
     const int lane = threadIdx.x & 31;
     double acc = 0.0;
     for (int t = lane; t < P.N; t += 32) {
         double term = 0.0;
-        if (t < P.n1) {
-            const int a = rowmatch[t];
-            term = (double)(M ? M[t * P.C + a] : node_cost_at(P, sm, t, a));
-        } else {
+        if (t < P.n1) term = (double)node_cost_at(P, sm, t, rowmatch[t]);
+        else {
             const int a = t - P.n1;
-            if (colmatch[a] == P.n1) term = (double)(M ? M[P.n1 * P.C + a] : node_cost_at(P, sm, P.n1, a));
+            if (colmatch[a] == P.n1) term = (double)node_cost_at(P, sm, P.n1, a);
         }
         acc = __dadd_rn(acc, term);
     }
@@ -705,7 +574,7 @@ __device__ inline double score_assignment(const Pair &P, const Slice &sm, int nn
             }
     }
     preserved = __reduce_add_sync(kFull, preserved);
-    const double nodes = matched_sum(P, sm, nullptr, rowmatch, colmatch);
+    const double nodes = matched_node_cost(P, sm, rowmatch, colmatch);
     return __dadd_rn(nodes, (double)(nnz1 + nnz2 - 2 * preserved));
 }
 
@@ -727,12 +596,24 @@ __device__ inline int count_bits(const uint32_t *bits, int words)
     return __reduce_add_sync(kFull, c);
 }
 
-// heuristic_prediction_hun's node_cost_mat (ged_env.py:310-315) in closed form from node degrees.
-__device__ inline void init_cost_closed_form(const Pair &P, const Slice &sm, float *cost)
+// Route one element of an R x C cost matrix to where the LAP reads it from.  Every lane calls this for (i, lane + 32 t).
+template <int S, class Store>
+__device__ __forceinline__ void emit_cost(const Store &store, const Slice &sm, int n1, int n2, int i, int t, float c)
 {
+    const int a = (threadIdx.x & 31) + 32 * t;
+    if (i < n1) {
+        if (t < S) store.put(i, t, c);           // tcgen05.st is warp-collective: no lane predicate around it
+        if (a == n2) sm.cdel[i] = c;
+    } else if (a <= n2) sm.cins[a] = c;
+}
+
+// heuristic_prediction_hun's node_cost_mat (ged_env.py:310-315) in closed form from node degrees.
+template <int S, class Store>
+__device__ inline void init_cost_closed_form(const Pair &P, const Slice &sm, const Store &store, float *trace)
+{
+    constexpr int T = S + 1;
     const int lane = threadIdx.x & 31;
-    // degrees into rs / cs (as floats; small integers)
-    for (int i = lane; i < P.R; i += 32) {
+    for (int i = lane; i < P.R; i += 32) {       // degrees into rs / cs (as floats; small integers)
         int d = 0;
         for (int w = 0; w < P.W1; ++w) d += __popc(sm.bits1[i * P.W1 + w]);
         sm.rs[i] = (float)d;
@@ -743,16 +624,23 @@ __device__ inline void init_cost_closed_form(const Pair &P, const Slice &sm, flo
         sm.cs[a] = (float)d;
     }
     __syncwarp();
-    for (int e = lane; e < P.R * P.C; e += 32) {
-        const int i = e / P.C, a = e - i * P.C;
-        const int d1 = (int)sm.rs[i], d2 = (int)sm.cs[a];
-        int val;
-        if (i < P.n1 && a < P.n2) { const int d = abs(d1 - d2) - 1; val = d > 0 ? d : 0; }
-        else if (i < P.n1) val = d1;
-        else if (a < P.n2) val = d2;
-        else val = 0;
-        cost[e] = (float)val;
+    for (int i = 0; i < P.R; ++i) {
+        const int d1 = (int)sm.rs[i];
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            if (32 * t >= P.C) break;
+            const int a = lane + 32 * t;
+            const int d2 = (a < P.C) ? (int)sm.cs[a] : 0;
+            int val;
+            if (i < P.n1 && a < P.n2) { const int d = abs(d1 - d2) - 1; val = d > 0 ? d : 0; }
+            else if (i < P.n1) val = d1;
+            else if (a < P.n2) val = d2;
+            else val = 0;
+            emit_cost<S>(store, sm, P.n1, P.n2, i, t, (float)val);
+            if (trace && a < P.C) trace[i * P.C + a] = (float)val;
+        }
     }
+    store.flush();
     __syncwarp();
 }
 
@@ -760,6 +648,172 @@ __device__ __forceinline__ float dense_b(const Pair &P, const int16_t *rowmatch,
 {
     if (i < P.n1) return (rowmatch[i] == a) ? 1.0f : 0.0f;
     return (a < P.n2 && colmatch[a] == P.n1) ? 1.0f : 0.0f;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// cost = K vec(X) from the factors (replaces torch.mm(k, v), ged_env.py:269):
+//     K vec(X) = A1 X M2^T + M1 X A2^T - 2 A1 X A2^T + Cn o X      (identity checked in the tests)
+// organised around Y = X A2^T (Y[j,a] = sum_{b in N2(a)} X[j,b], ascending b) so that every inner term is a ROW gather:
+// P[i,a] = sum_{j in N1(i)} X[j,a],  T3[i,a] = sum_{j in N1(i)} Y[j,a],  Q[i,a] = Y[i,a].
+//   pass A: each row of X goes through a small double-buffered shared-memory row buffer for the random column gathers
+//           of Y (neighbour lists of the lane's columns held in registers); row / column sums on the way; Y -> global;
+//   pass B: per result row, the neighbour rows of X and Y are read with coalesced, mutually independent loads (one L2
+//           round trip per row) and the row of cost goes straight to the LAP's cost store.
+// Fused into pass B: s_vv = <cost, X> (fp64, partial per lane = a & 31, rows ascending: canonical order v2), the
+// NaN / -inf check SciPy does on its input, and the optional trace copy.  T = number of 32-wide column tiles of a row.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void decode_neighbours(const uint32_t *row, int W, int (&nb)[kMaxDeg])
+{
+    int w = 0;
+    uint32_t word = row[0];
+#pragma unroll
+    for (int k = 0; k < kMaxDeg; ++k) {
+        while (word == 0u && w + 1 < W) word = row[++w];
+        nb[k] = word ? (w * 32 + __ffs(word) - 1) : -1;
+        word &= word - 1u;
+    }
+}
+
+template <int S, class Store>
+__device__ void kv_apply(const Pair &P, const Slice &sm, const float *X, float *Y, const Store &store, float *trace,
+                         double &s_vv_out, bool &invalid_out)
+{
+    constexpr int T = S + 1;
+    const int lane = threadIdx.x & 31;
+    const int R = P.R, C = P.C, n1 = P.n1, n2 = P.n2;
+    const bool fast = P.maxdeg <= kMaxDeg;
+    const int rbs = (C + 3) & ~3;                              // row-buffer stride
+
+    // ---- pass A --------------------------------------------------------------------------------------------------
+    int nb2[T][kMaxDeg];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        const int a = lane + 32 * t;
+#pragma unroll
+        for (int k = 0; k < kMaxDeg; ++k) nb2[t][k] = -1;
+        if (fast && a < C) decode_neighbours(sm.bits2 + a * P.W2, P.W2, nb2[t]);
+    }
+    float csacc[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) csacc[t] = 0.0f;
+    for (int j = 0; j < R; ++j) {
+        float *buf = sm.rowbuf + (j & 1) * rbs;
+        float part = 0.0f;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const int a = lane + 32 * t;
+            if (a < C) {
+                const float x = X[j * C + a];
+                buf[a] = x;
+                csacc[t] = __fadd_rn(csacc[t], x);
+                part = __fadd_rn(part, x);
+            }
+        }
+        part = warp_butterfly(part);
+        if (lane == 0) sm.rs[j] = part;
+        __syncwarp();                                          // row buffer written -> gathers below
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const int a = lane + 32 * t;
+            if (a < C) {
+                float in = 0.0f;
+                if (fast) {
+#pragma unroll
+                    for (int k = 0; k < kMaxDeg; ++k) if (nb2[t][k] >= 0) in = __fadd_rn(in, buf[nb2[t][k]]);
+                } else {
+                    for (int w = 0; w < P.W2; ++w) {
+                        uint32_t word = sm.bits2[a * P.W2 + w];
+                        while (word) { const int b = w * 32 + __ffs(word) - 1; word &= word - 1; in = __fadd_rn(in, buf[b]); }
+                    }
+                }
+                Y[j * C + a] = in;
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) { const int a = lane + 32 * t; if (a < C) sm.cs[a] = csacc[t]; }
+    __syncwarp();
+    for (int i = lane; i < R; i += 32) {                       // rsP[i] = sum_{j in N1(i)} rs[j]
+        float s = 0.0f;
+        for (int w = 0; w < P.W1; ++w) {
+            uint32_t word = sm.bits1[i * P.W1 + w];
+            while (word) { const int j = w * 32 + __ffs(word) - 1; word &= word - 1; s = __fadd_rn(s, sm.rs[j]); }
+        }
+        sm.rsP[i] = s;
+    }
+    float csq[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {                              // csQ[a] = sum_{b in N2(a)} cs[b]   (kept in registers)
+        const int a = lane + 32 * t;
+        float s = 0.0f;
+        if (a < C)
+            for (int w = 0; w < P.W2; ++w) {
+                uint32_t word = sm.bits2[a * P.W2 + w];
+                while (word) { const int b = w * 32 + __ffs(word) - 1; word &= word - 1; s = __fadd_rn(s, sm.cs[b]); }
+            }
+        csq[t] = s;
+    }
+    __syncwarp();
+
+    // ---- pass B --------------------------------------------------------------------------------------------------
+    double svv = 0.0;
+    bool bad = false;
+    for (int i = 0; i < R; ++i) {
+        int nb[kMaxDeg];
+#pragma unroll
+        for (int k = 0; k < kMaxDeg; ++k) nb[k] = -1;
+        if (fast) decode_neighbours(sm.bits1 + i * P.W1, P.W1, nb);      // warp-uniform
+        const float rsPi = sm.rsP[i];
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            if (32 * t >= C) break;
+            const int a = lane + 32 * t;
+            const bool in_row = a < C;
+            float Pv = 0.0f, T3 = 0.0f, xia = 0.0f, Qv = 0.0f;
+            if (in_row) {
+                xia = X[i * C + a];
+                Qv = Y[i * C + a];
+                if (fast) {
+                    float xv[kMaxDeg], yv[kMaxDeg];
+#pragma unroll
+                    for (int k = 0; k < kMaxDeg; ++k) {          // all loads first: they are independent
+                        xv[k] = 0.0f;
+                        yv[k] = 0.0f;
+                        if (nb[k] >= 0) { xv[k] = X[nb[k] * C + a]; yv[k] = Y[nb[k] * C + a]; }
+                    }
+#pragma unroll
+                    for (int k = 0; k < kMaxDeg; ++k)
+                        if (nb[k] >= 0) { Pv = __fadd_rn(Pv, xv[k]); T3 = __fadd_rn(T3, yv[k]); }
+                } else {
+                    for (int w = 0; w < P.W1; ++w) {
+                        uint32_t word = sm.bits1[i * P.W1 + w];
+                        while (word) {
+                            const int j = w * 32 + __ffs(word) - 1;
+                            word &= word - 1;
+                            Pv = __fadd_rn(Pv, X[j * C + a]);
+                            T3 = __fadd_rn(T3, Y[j * C + a]);
+                        }
+                    }
+                }
+            }
+            const float t1 = (a < n2) ? __fsub_rn(rsPi, Pv) : rsPi;
+            const float t2 = (i < n1) ? __fsub_rn(csq[t], Qv) : csq[t];
+            float sres = __fadd_rn(t1, t2);
+            sres = __fsub_rn(sres, __fadd_rn(T3, T3));
+            const float d = in_row ? __fmul_rn(node_cost_at(P, sm, i, a), xia) : 0.0f;
+            const float c = __fadd_rn(sres, d);
+            emit_cost<S>(store, sm, n1, n2, i, t, c);
+            if (in_row) {
+                svv = __dadd_rn(svv, __dmul_rn((double)c, (double)xia));
+                if (!(i == n1 && a == n2)) bad |= (c != c) || (c == -INFINITY);
+                if (trace) trace[i * C + a] = c;
+            }
+        }
+    }
+    store.flush();
+    __syncwarp();
+    s_vv_out = warp_butterfly(svv);
+    invalid_out = __any_sync(kFull, bad);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -778,11 +832,12 @@ struct SolveParams {
     float *workspace;
     const int32_t *order;
     int count;
+    int tmem_warps;          // 0 or 4: warps 0..3 of every CTA keep their cost matrix in tensor memory
+    int tmem_cols;           // columns allocated per CTA (power of two >= 32)
     ged_solve_out out;
     SliceLayout layout;
 };
 
-template <int S>
 __device__ inline void load_pair(const ged_pairs &pp, int p, const Slice &sm, Pair &P, int &status)
 {
     const int lane = threadIdx.x & 31;
@@ -803,24 +858,20 @@ __device__ inline void load_pair(const ged_pairs &pp, int p, const Slice &sm, Pa
         for (int a = lane; a < P.n2; a += 32) sm.lab2[a] = l2[a];
     }
     __syncwarp();
+    P.maxdeg = max_degree(sm.bits1, P.R, P.W1, sm.bits2, P.C, P.W2);
 }
 
-template <int S>
-__global__ void ged_solve_kernel(SolveParams prm)
+// One candidate solve by one warp: GEDenv.step :110-124 -> solve_feasible_ged :140-158 -> ipfp_ged :256-289.
+template <int S, class Store>
+__device__ void solve_one(const SolveParams &prm, int b, const Slice &sm, const Store &store)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int slot = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (slot >= prm.count) return;
-    const int b = prm.order ? prm.order[slot] : slot;
-    const Slice sm = carve(smem_raw + (size_t)warp * prm.layout.bytes, prm.layout);
+    const int lane = threadIdx.x & 31;
     const ged_solve_out &out = prm.out;
-
     const int p = prm.base_idx ? prm.base_idx[b] : b;
     Pair P;
     int status = 0;
-    load_pair<S>(prm.pairs, p, sm, P, status);
-    const int n1 = P.n1, n2 = P.n2, RC = P.R * P.C;
+    load_pair(prm.pairs, p, sm, P, status);
+    const int n1 = P.n1, n2 = P.n2;
 
     // GEDenv.step edge toggle (ged_env.py:110-121)
     int eu = prm.edit_u ? prm.edit_u[b] : -1, ev = prm.edit_v ? prm.edit_v[b] : -1;
@@ -837,12 +888,12 @@ __global__ void ged_solve_kernel(SolveParams prm)
             w_vu = was_present ? (w_vu & ~m_vu) : (w_vu | m_vu);
         }
         __syncwarp();
+        P.maxdeg = max_degree(sm.bits1, P.R, P.W1, sm.bits2, P.C, P.W2);
     }
     const int nnz1 = count_bits(sm.bits1, P.R * P.W1), nnz2 = count_bits(sm.bits2, P.C * P.W2);
-    P.maxdeg = max_degree(sm.bits1, P.R, P.W1, sm.bits2, P.C, P.W2);
 
-    float *X = prm.workspace + (long long)b * 2 * prm.mat_stride;        // fractional iterate
-    float *Y = X + prm.mat_stride;                                       // X A2^T scratch of kv_apply
+    float *X = prm.workspace ? prm.workspace + (long long)b * 2 * prm.mat_stride : nullptr;   // fractional iterate
+    float *Y = X ? X + prm.mat_stride : nullptr;                                              // X A2^T scratch of kv_apply
     unsigned long long lap_steps = 0;
     int iters = 0;
     double best_ub = INFINITY;
@@ -854,16 +905,14 @@ __global__ void ged_solve_kernel(SolveParams prm)
     if (status == 0) {
         if (prm.x_init) {
             const float *x0 = prm.x_init + (long long)b * prm.mat_stride;
-            for (int e = lane; e < RC; e += 32) X[e] = x0[e];
+            for (int e = lane; e < P.R * P.C; e += 32) X[e] = x0[e];
             for (int i = lane; i < n1; i += 32) sm.bestrow[i] = (int16_t)n2;
             for (int a = lane; a < n2; a += 32) sm.bestcol[a] = (int16_t)n1;
             __syncwarp();
         } else {
             // hungarian_ged (ged_env.py:303-326): v0 = LSAPE(node_cost_mat)
-            init_cost_closed_form(P, sm, sm.cost);
-            if (out.tr_init_cost)
-                for (int e = lane; e < RC; e += 32) out.tr_init_cost[(long long)b * prm.mat_stride + e] = sm.cost[e];
-            status |= lsape_warp<S>(sm.cost, n1, n2, sm, &lap_steps);
+            init_cost_closed_form<S>(P, sm, store, out.tr_init_cost ? out.tr_init_cost + (long long)b * prm.mat_stride : nullptr);
+            status |= lsape_warp<S>(store, false, n1, n2, sm, &lap_steps);
             if (status == 0) {
                 for (int i = lane; i < n1; i += 32) {
                     sm.bestrow[i] = sm.rowmatch[i];
@@ -885,22 +934,18 @@ __global__ void ged_solve_kernel(SolveParams prm)
     if (status == 0 && prm.solver_kind == GED_SOLVER_IPFP) {
         for (int it = 0; it < prm.max_iter; ++it) {
             iters = it + 1;
+            double s_vv;                                                 // = last_v^T K last_v, ged_env.py:283
+            bool invalid;
 #ifdef GED_TIMING
             const long long tk0 = clock64();
 #endif
-            kv_apply<S>(P, sm, X, Y, sm.cost);                           // ged_env.py:269
+            kv_apply<S>(P, sm, X, Y, store, out.tr_cost ? out.tr_cost + ((long long)b * prm.max_iter + it) * prm.mat_stride : nullptr,
+                        s_vv, invalid);                                  // ged_env.py:269
 #ifdef GED_TIMING
             t_kv += clock64() - tk0;
-#endif
-            const double s_vv = dot_flat(sm.cost, X, RC);                // = last_v^T K last_v, ged_env.py:283
-            if (out.tr_cost) {
-                float *dst = out.tr_cost + ((long long)b * prm.max_iter + it) * prm.mat_stride;
-                for (int e = lane; e < RC; e += 32) dst[e] = sm.cost[e];
-            }
-#ifdef GED_TIMING
             const long long tl0 = clock64();
 #endif
-            status |= lsape_warp<S>(sm.cost, n1, n2, sm, &lap_steps);   // ged_env.py:270
+            status |= lsape_warp<S>(store, invalid, n1, n2, sm, &lap_steps);   // ged_env.py:270
 #ifdef GED_TIMING
             t_lap += clock64() - tl0;
 #endif
@@ -911,23 +956,25 @@ __global__ void ged_solve_kernel(SolveParams prm)
                 for (int i = lane; i < n1; i += 32) sm.bestrow[i] = sm.rowmatch[i];
                 for (int a = lane; a < n2; a += 32) sm.bestcol[a] = sm.colmatch[a];
             }
-            const double s_vb = matched_sum(P, sm, sm.cost, sm.rowmatch, sm.colmatch);
+            const double s_vb = matched_cost_sum<S>(store, sm, n1, n2);
             const double alpha = __dsub_rn(s_vb, s_vv);                  // :275 (K symmetric: v^T K = (K v)^T)
             const double beta = __dadd_rn(__dsub_rn(ub, __dadd_rn(s_vb, s_vb)), s_vv);   // :277
             const double t0 = __ddiv_rn(-alpha, beta);                   // :278
             const float t0f = (float)t0;
             const bool jump = (beta <= 0.0) || (t0f >= 1.0f);            // :279
             float *trx = out.tr_x_after ? out.tr_x_after + ((long long)b * prm.max_iter + it) * prm.mat_stride : nullptr;
-            for (int i = 0; i < P.R; ++i)
+            for (int i = 0; i < P.R; ++i) {
+                const int rm = (i < n1) ? sm.rowmatch[i] : -1;
                 for (int a = lane; a < P.C; a += 32) {
                     const int e = i * P.C + a;
-                    const float bv = dense_b(P, sm.rowmatch, sm.colmatch, i, a);
+                    const float bv = (i < n1) ? ((rm == a) ? 1.0f : 0.0f) : ((a < n2 && sm.colmatch[a] == n1) ? 1.0f : 0.0f);
                     float xn;
                     if (jump) xn = bv;                                   // :280
                     else { const float x = X[e]; xn = __fadd_rn(x, __fmul_rn(t0f, __fsub_rn(bv, x))); }   // :282
                     X[e] = xn;
                     if (trx) trx[e] = xn;
                 }
+            }
             if (out.tr_scalars && lane == 0) {
                 double *d = out.tr_scalars + ((long long)b * prm.max_iter + it) * 6;
                 d[0] = s_vv; d[1] = s_vb; d[2] = ub; d[3] = alpha; d[4] = beta; d[5] = t0;
@@ -967,9 +1014,9 @@ __global__ void ged_solve_kernel(SolveParams prm)
         }
     }
 #ifdef GED_TIMING
-    if (lane == 0) printf("solve %d: total %lld cycles, lap %lld (%.1f%%), kv %lld (%.1f%%), lap steps %llu -> %.1f cycles/step\n", b,
-                          clock64() - t_begin, t_lap, 100.0 * t_lap / (clock64() - t_begin), t_kv, 100.0 * t_kv / (clock64() - t_begin),
-                          lap_steps, (double)t_lap / (double)lap_steps);
+    if (lane == 0) printf("solve %d (%s): total %lld cycles, lap %lld (%.1f%%), kv %lld (%.1f%%), lap steps %llu -> %.1f cycles/step\n", b,
+                          Store::kPrefetch ? "smem" : "tmem", clock64() - t_begin, t_lap, 100.0 * t_lap / (clock64() - t_begin), t_kv,
+                          100.0 * t_kv / (clock64() - t_begin), lap_steps, (double)t_lap / (double)lap_steps);
 #endif
     if (lane == 0) {
         out.ged[b] = ged_base;
@@ -989,7 +1036,58 @@ __global__ void ged_solve_kernel(SolveParams prm)
     }
 }
 
-// ---- stand-alone stages ---------------------------------------------------------------------------------------
+// CTA = [tmem_warps TMEM-backed solves][remaining warps: shared-memory-backed solves].  Dynamic shared memory:
+// tmem_warps slices without a cost block, then the others with one.
+// TM = false: no tensor-memory instruction in the binary at all (a CTA of a kernel that may allocate tensor memory holds
+// the SM's allocation permit until it relinquishes it, which keeps other CTAs off the SM).
+template <int S, bool TM>
+__global__ void ged_solve_kernel(SolveParams prm)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t tmem_base_slot;
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int nt = TM ? prm.tmem_warps : 0;
+    uint32_t tmem_base = 0;
+    if constexpr (TM) {                      // the only CTA-wide synchronisation: tensor-memory allocation
+        if (warp == 0) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tmem_base_slot);
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "r"((uint32_t)prm.tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tmem_base = tmem_base_slot;
+    }
+    const int slot = blockIdx.x * nwarps + warp;
+    if (slot < prm.count) {
+        const int b = prm.order ? prm.order[slot] : slot;
+        const int m1 = prm.pairs.max_n1, m2 = prm.pairs.max_n2;
+        bool done = false;
+        if constexpr (TM) {
+            if (warp < nt) {
+                const Slice sm = carve(smem_raw + (size_t)warp * prm.layout.bytes, prm.layout, m1, m2, false);
+                TmemCost<S> store{tmem_base + ((uint32_t)(32 * warp) << 16)};
+                solve_one<S>(prm, b, sm, store);
+                done = true;
+            }
+        }
+        if (!done) {
+            unsigned char *base = smem_raw + (size_t)nt * prm.layout.bytes + (size_t)(warp - nt) * (prm.layout.bytes + prm.layout.cost_bytes);
+            const Slice sm = carve(base, prm.layout, m1, m2, true);
+            SmemCost<S> store{sm.cost, prm.pairs.n2[prm.base_idx ? prm.base_idx[b] : b]};
+            solve_one<S>(prm, b, sm, store);
+        }
+    }
+    if constexpr (TM) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)prm.tmem_cols) : "memory");
+    }
+}
+
+// ---- stand-alone stages (shared-memory cost store) ----------------------------------------------------------------
 struct LsapeParams {
     int B;
     const int32_t *n1, *n2;
@@ -999,6 +1097,7 @@ struct LsapeParams {
     int ms1, ms2;
     float *lb;
     int32_t *status;
+    int max_n1, max_n2;
     SliceLayout layout;
 };
 
@@ -1006,22 +1105,32 @@ template <int S>
 __global__ void ged_lsape_kernel(LsapeParams prm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int T = S + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.x * (blockDim.x >> 5) + warp;
     if (b >= prm.B) return;
-    const Slice sm = carve(smem_raw + (size_t)warp * prm.layout.bytes, prm.layout);
-    const int n1 = prm.n1[b], n2 = prm.n2[b], C = n2 + 1, RC = (n1 + 1) * C;
+    const Slice sm = carve(smem_raw + (size_t)warp * (prm.layout.bytes + prm.layout.cost_bytes), prm.layout, prm.max_n1, prm.max_n2, true);
+    const int n1 = prm.n1[b], n2 = prm.n2[b], C = n2 + 1;
+    SmemCost<S> store{sm.cost, n2};
     const float *src = prm.cost + (long long)b * prm.mat_stride;
-    for (int e = lane; e < RC; e += 32) sm.cost[e] = src[e];
-    __syncwarp();
-    const int st = lsape_warp<S>(sm.cost, n1, n2, sm, nullptr);
+    bool bad = false;
+    for (int i = 0; i <= n1; ++i)
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            if (32 * t >= C) break;
+            const int a = lane + 32 * t;
+            const float c = (a < C) ? src[i * C + a] : 0.0f;
+            if (a < C && !(i == n1 && a == n2)) bad |= (c != c) || (c == -INFINITY);
+            emit_cost<S>(store, sm, n1, n2, i, t, c);
+        }
+    store.flush();
+    const bool invalid = __any_sync(kFull, bad);
+    const int st = lsape_warp<S>(store, invalid, n1, n2, sm, nullptr);
     if (st == 0) {
         for (int i = lane; i < n1; i += 32) prm.rowmatch[(long long)b * prm.ms1 + i] = sm.rowmatch[i];
         for (int a = lane; a < n2; a += 32) prm.colmatch[(long long)b * prm.ms2 + a] = sm.colmatch[a];
         if (prm.lb) {
-            Pair P;
-            P.n1 = n1; P.n2 = n2; P.R = n1 + 1; P.C = C; P.N = n1 + n2; P.W1 = P.W2 = 1; P.node_cost = nullptr;
-            const double s = matched_sum(P, sm, sm.cost, sm.rowmatch, sm.colmatch);   // ged_env.py:349
+            const double s = matched_cost_sum<S>(store, sm, n1, n2);     // ged_env.py:349
             if (lane == 0) prm.lb[b] = (float)s;
         }
     } else if (prm.lb && lane == 0) prm.lb[b] = NAN;
@@ -1032,6 +1141,7 @@ struct KvParams {
     ged_pairs pairs;
     const float *x;
     float *cost;
+    float *scratch;          // Y = X A2^T scratch, same layout as x / cost
     long long mat_stride;
     SliceLayout layout;
 };
@@ -1040,20 +1150,22 @@ template <int S>
 __global__ void ged_kv_kernel(KvParams prm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warp = threadIdx.x >> 5;
     const int b = blockIdx.x * (blockDim.x >> 5) + warp;
     if (b >= prm.pairs.num_pairs) return;
-    const Slice sm = carve(smem_raw + (size_t)warp * prm.layout.bytes, prm.layout);
+    const Slice sm = carve(smem_raw + (size_t)warp * (prm.layout.bytes + prm.layout.cost_bytes), prm.layout, prm.pairs.max_n1,
+                           prm.pairs.max_n2, true);
     Pair P;
     int status = 0;
-    load_pair<S>(prm.pairs, b, sm, P, status);
-    P.maxdeg = max_degree(sm.bits1, P.R, P.W1, sm.bits2, P.C, P.W2);
-    float *dst = prm.cost + (long long)b * prm.mat_stride;
-    kv_apply<S>(P, sm, prm.x + (long long)b * prm.mat_stride, dst, sm.cost);      // the output buffer doubles as Y scratch
-    __syncwarp();
-    for (int e = lane; e < P.R * P.C; e += 32) dst[e] = sm.cost[e];
+    load_pair(prm.pairs, b, sm, P, status);
+    SmemCost<S> store{sm.cost, P.n2};
+    double s_vv;
+    bool invalid;
+    kv_apply<S>(P, sm, prm.x + (long long)b * prm.mat_stride, prm.scratch + (long long)b * prm.mat_stride, store,
+                prm.cost + (long long)b * prm.mat_stride, s_vv, invalid);         // the result is taken from the trace hook
 }
 
+#ifndef GED_TU_S
 struct ScoreParams {
     ged_pairs pairs;
     int B;
@@ -1063,17 +1175,16 @@ struct ScoreParams {
     SliceLayout layout;
 };
 
-template <int S>
 __global__ void ged_score_kernel(ScoreParams prm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.x * (blockDim.x >> 5) + warp;
     if (b >= prm.B) return;
-    const Slice sm = carve(smem_raw + (size_t)warp * prm.layout.bytes, prm.layout);
+    const Slice sm = carve(smem_raw + (size_t)warp * prm.layout.bytes, prm.layout, prm.pairs.max_n1, prm.pairs.max_n2, false);
     Pair P;
     int status = 0;
-    load_pair<S>(prm.pairs, prm.base_idx ? prm.base_idx[b] : b, sm, P, status);
+    load_pair(prm.pairs, prm.base_idx ? prm.base_idx[b] : b, sm, P, status);
     for (int i = lane; i < P.n1; i += 32) sm.rowmatch[i] = (int16_t)prm.rowmatch[(long long)b * prm.ms1 + i];
     for (int a = lane; a < P.n2; a += 32) sm.colmatch[a] = (int16_t)prm.colmatch[(long long)b * prm.ms2 + a];
     __syncwarp();
@@ -1140,60 +1251,138 @@ __global__ void ged_quadform_final_kernel(const float *partial, int ctas_per_mat
     out[b] = s;
 }
 
+#endif  // !GED_TU_S
+
 // ---------------------------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------------------------
-int slots_for(int max_n1, int max_n2)
+static int slots_for(int max_n1, int max_n2)
 {
     const int m = max_n1 > max_n2 ? max_n1 : max_n2;
     const int S = (m + 31) / 32;
     return S < 1 ? 1 : S;
 }
 
-int warps_per_block_for(int slice_bytes)
+static int env_int(const char *name, int dflt)
 {
-    static int override_wpb = -1;
-    if (override_wpb < 0) {
-        const char *e = getenv("GED_B200_WARPS_PER_BLOCK");
-        override_wpb = e ? atoi(e) : 0;
-    }
-    if (override_wpb > 0) return override_wpb;
-    // one warp per CTA keeps CTA granularity minimal; 32 CTAs/SM is the hardware cap, so for slices small enough
-    // that more than 32 would fit, pack two warps per CTA
-    return (slice_bytes + 1024) * 32 <= kMaxSmemBytes / 2 ? 2 : 1;
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
 }
 
+// Stand-alone stage kernels: all warps of a CTA have identical slices.
 template <typename KernelT, typename ParamsT>
-int launch_sized(KernelT kernel, const ParamsT &prm, int count, int slice_bytes, cudaStream_t stream, const char *name)
+int launch_uniform(KernelT kernel, const ParamsT &prm, int count, int slice_bytes, cudaStream_t stream, const char *name)
 {
-    int wpb = warps_per_block_for(slice_bytes);
-    while (wpb > 1 && (long long)wpb * slice_bytes > kMaxSmemBytes) --wpb;
-    static int pad = -1;                    // occupancy experiments only: extra dynamic shared memory per CTA
-    if (pad < 0) { const char *e = getenv("GED_B200_SMEM_PAD"); pad = e ? atoi(e) : 0; }
-    const int smem = wpb * slice_bytes + pad;
+    int wpb = (slice_bytes + 1024) * 32 <= kMaxSmemBytes / 2 ? 2 : 1;      // 32 CTAs/SM is the hardware cap
+    const int smem = wpb * slice_bytes;
     if (smem > kMaxSmemBytes) return fail(GED_E_TOO_LARGE, "pair too large for one warp's shared-memory slice");
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail_cuda(e, name);
-    const int blocks = (count + wpb - 1) / wpb;
-    kernel<<<blocks, wpb * 32, smem, stream>>>(prm);
+    kernel<<<(count + wpb - 1) / wpb, wpb * 32, smem, stream>>>(prm);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(e, name);
     return GED_OK;
 }
 
-#define GED_DISPATCH_S(S_, KERNEL, ...)                                                                \
-    switch (S_) {                                                                                      \
-    case 1: return launch_sized(KERNEL<1>, __VA_ARGS__);                                               \
-    case 2: return launch_sized(KERNEL<2>, __VA_ARGS__);                                               \
-    case 3: return launch_sized(KERNEL<3>, __VA_ARGS__);                                               \
-    case 4: return launch_sized(KERNEL<4>, __VA_ARGS__);                                               \
-    case 5: return launch_sized(KERNEL<5>, __VA_ARGS__);                                               \
-    case 6: return launch_sized(KERNEL<6>, __VA_ARGS__);                                               \
-    case 7: return launch_sized(KERNEL<7>, __VA_ARGS__);                                               \
-    default: return fail(GED_E_TOO_LARGE, "graphs above 224 nodes are not supported by this build");   \
+// Shape of the hybrid CTA of the solve kernel (see the file header): 4 tensor-memory-backed warps + k shared-memory-
+// backed warps, sized so that shared memory and tensor-memory columns run out together.
+struct CtaShape { int tmem_warps, tmem_cols, smem_warps, smem_bytes; };
+
+static CtaShape plan_cta(const SliceLayout &L, int max_n1, int S, int regs_per_thread)
+{
+    CtaShape c{0, 0, 1, 0};
+    const int big = L.bytes + L.cost_bytes;
+    const int mode = env_int("GED_B200_COST_STORE", 2);        // 0: shared memory only, 1: tensor memory only, 2: hybrid
+    int cols = 32;
+    while (cols < max_n1 * S) cols <<= 1;
+    const int max_warps_by_regs = 65536 / (32 * ((regs_per_thread + 7) / 8 * 8));
+    if (mode != 0 && cols <= 512) {
+        const int q = 512 / cols;                              // CTAs per SM that tensor memory can serve
+        const int budget = kMaxSmemBytes / q - 1024;           // shared memory per CTA (static + reserved included)
+        int k = (budget - kTmemWarps * L.bytes) / big;
+        if (budget < kTmemWarps * L.bytes) k = -1;
+        if (mode == 1 && k > 0) k = 0;
+        const int kmax = max_warps_by_regs / q - kTmemWarps;
+        if (k > kmax) k = kmax;
+        const int kforce = env_int("GED_B200_SMEM_WARPS", -1);
+        if (kforce >= 0 && kforce <= k) k = kforce;
+        if (k >= 0) {
+            c.tmem_warps = kTmemWarps;
+            c.tmem_cols = cols;
+            c.smem_warps = k;
+            c.smem_bytes = kTmemWarps * L.bytes + k * big;
+            return c;
+        }
+    }
+    // shared memory only: one warp per CTA keeps CTA granularity minimal; pack two when > 32 CTAs would fit
+    c.smem_warps = (big + 1024) * 32 <= kMaxSmemBytes / 2 ? 2 : 1;
+    c.smem_bytes = c.smem_warps * big;
+    return c;
+}
+
+template <int S, bool TM>
+int launch_solve_as(SolveParams prm, const CtaShape &c, cudaStream_t stream)
+{
+    prm.tmem_warps = c.tmem_warps;
+    prm.tmem_cols = c.tmem_cols;
+    const int wpb = c.tmem_warps + c.smem_warps;
+    cudaError_t e = cudaFuncSetAttribute(ged_solve_kernel<S, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes);
+    if (e != cudaSuccess) return fail_cuda(e, "ged_solve_batch");
+    if (env_int("GED_B200_VERBOSE", 0))
+        fprintf(stderr, "[ged_b200] solve<S=%d> count=%d max_n=(%d,%d) cta: %d tmem warps (%d cols) + %d smem warps, %d B dynamic smem\n",
+                S, prm.count, prm.pairs.max_n1, prm.pairs.max_n2, c.tmem_warps, c.tmem_cols, c.smem_warps, c.smem_bytes);
+    ged_solve_kernel<S, TM><<<(prm.count + wpb - 1) / wpb, wpb * 32, c.smem_bytes, stream>>>(prm);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(e, "ged_solve_batch");
+    return GED_OK;
+}
+
+template <int S>
+int launch_solve(const SolveParams &prm, cudaStream_t stream)
+{
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, ged_solve_kernel<S, true>);
+    if (e != cudaSuccess) return fail_cuda(e, "ged_solve_batch");
+    const CtaShape c = plan_cta(prm.layout, prm.pairs.max_n1, S, fa.numRegs);
+    if (c.smem_bytes > kMaxSmemBytes) return fail(GED_E_TOO_LARGE, "pair too large for one warp's shared-memory slice");
+    return c.tmem_warps > 0 ? launch_solve_as<S, true>(prm, c, stream) : launch_solve_as<S, false>(prm, c, stream);
+}
+
+// ---- per-S entry points (one translation unit each) and their dispatch ---------------------------------------------------
+#define GED_CAT_(a, b) a##b
+#define GED_CAT(a, b) GED_CAT_(a, b)
+#define GED_DECLARE_S(k)                                                  \
+    int GED_CAT(launch_solve_s, k)(const SolveParams &, cudaStream_t);    \
+    int GED_CAT(launch_lsape_s, k)(const LsapeParams &, cudaStream_t);    \
+    int GED_CAT(launch_kv_s, k)(const KvParams &, cudaStream_t);
+GED_DECLARE_S(1) GED_DECLARE_S(2) GED_DECLARE_S(3) GED_DECLARE_S(4) GED_DECLARE_S(5) GED_DECLARE_S(6) GED_DECLARE_S(7)
+
+#ifdef GED_TU_S
+int GED_CAT(launch_solve_s, GED_TU_S)(const SolveParams &prm, cudaStream_t stream) { return launch_solve<GED_TU_S>(prm, stream); }
+int GED_CAT(launch_lsape_s, GED_TU_S)(const LsapeParams &prm, cudaStream_t stream)
+{
+    return launch_uniform(ged_lsape_kernel<GED_TU_S>, prm, prm.B, prm.layout.bytes + prm.layout.cost_bytes, stream, "ged_lsape_batch");
+}
+int GED_CAT(launch_kv_s, GED_TU_S)(const KvParams &prm, cudaStream_t stream)
+{
+    return launch_uniform(ged_kv_kernel<GED_TU_S>, prm, prm.pairs.num_pairs, prm.layout.bytes + prm.layout.cost_bytes, stream, "ged_kv_batch");
+}
+#else
+thread_local char g_err[512] = "";
+
+#define GED_DISPATCH_S(S_, NAME, ...)                                                                   \
+    switch (S_) {                                                                                       \
+    case 1: return GED_CAT(NAME, 1)(__VA_ARGS__);                                                       \
+    case 2: return GED_CAT(NAME, 2)(__VA_ARGS__);                                                       \
+    case 3: return GED_CAT(NAME, 3)(__VA_ARGS__);                                                       \
+    case 4: return GED_CAT(NAME, 4)(__VA_ARGS__);                                                       \
+    case 5: return GED_CAT(NAME, 5)(__VA_ARGS__);                                                       \
+    case 6: return GED_CAT(NAME, 6)(__VA_ARGS__);                                                       \
+    case 7: return GED_CAT(NAME, 7)(__VA_ARGS__);                                                       \
+    default: return fail(GED_E_TOO_LARGE, "graphs above 224 nodes are not supported by this build");    \
     }
 
-int check_pairs(const ged_pairs &p)
+static int check_pairs(const ged_pairs &p)
 {
     if (p.num_pairs < 0 || p.max_n1 < 1 || p.max_n2 < 1) return fail(GED_E_BADARG, "ged_pairs: bad sizes");
     if (p.num_pairs > 0 && (!p.n1 || !p.n2 || !p.adj1 || !p.adj2 || !p.adj1_off || !p.adj2_off))
@@ -1205,7 +1394,15 @@ int check_pairs(const ged_pairs &p)
     return GED_OK;
 }
 
-}  // namespace
+static int dispatch_solve(int S, const SolveParams &prm, cudaStream_t stream) { GED_DISPATCH_S(S, launch_solve_s, prm, stream) }
+static int dispatch_lsape(int S, const LsapeParams &prm, cudaStream_t stream) { GED_DISPATCH_S(S, launch_lsape_s, prm, stream) }
+static int dispatch_kv(int S, const KvParams &prm, cudaStream_t stream) { GED_DISPATCH_S(S, launch_kv_s, prm, stream) }
+#endif  // GED_TU_S
+
+}  // namespace ged_impl
+
+#ifndef GED_TU_S
+using namespace ged_impl;
 
 extern "C" {
 
@@ -1224,6 +1421,7 @@ int ged_solve_batch(const ged_solve_desc *d, const ged_solve_out *o, void *strea
     const long long need = (long long)(d->pairs.max_n1 + 1) * (d->pairs.max_n2 + 1);
     if (d->mat_stride < need) return fail(GED_E_BADARG, "ged_solve_batch: mat_stride < (max_n1+1)*(max_n2+1)");
     if (d->solver_kind == GED_SOLVER_IPFP && !d->workspace) return fail(GED_E_BADARG, "ged_solve_batch: workspace required for IPFP");
+    if (d->x_init && !d->workspace) return fail(GED_E_BADARG, "ged_solve_batch: workspace required with x_init");
     SolveParams prm;
     prm.pairs = d->pairs;
     prm.B = d->B;
@@ -1242,10 +1440,11 @@ int ged_solve_batch(const ged_solve_desc *d, const ged_solve_out *o, void *strea
     prm.count = d->order ? d->order_count : d->B;
     if (prm.count < 0 || prm.count > d->B) return fail(GED_E_BADARG, "ged_solve_batch: order_count out of range");
     if (prm.count == 0) return GED_OK;
+    prm.tmem_warps = 0;
+    prm.tmem_cols = 0;
     prm.out = *o;
     prm.layout = make_layout(d->pairs.max_n1, d->pairs.max_n2);
-    const int S = slots_for(d->pairs.max_n1, d->pairs.max_n2);
-    GED_DISPATCH_S(S, ged_solve_kernel, prm, prm.count, prm.layout.bytes, (cudaStream_t)stream, "ged_solve_batch")
+    return dispatch_solve(slots_for(d->pairs.max_n1, d->pairs.max_n2), prm, (cudaStream_t)stream);
 }
 
 int ged_lsape_batch(int32_t B, const int32_t *n1, const int32_t *n2, int32_t max_n1, int32_t max_n2,
@@ -1257,20 +1456,18 @@ int ged_lsape_batch(int32_t B, const int32_t *n1, const int32_t *n2, int32_t max
     if (!n1 || !n2 || !cost || !rowmatch || !colmatch) return fail(GED_E_BADARG, "ged_lsape_batch: null pointer");
     if (ms1 < max_n1 || ms2 < max_n2 || mat_stride < (int64_t)(max_n1 + 1) * (max_n2 + 1)) return fail(GED_E_BADARG, "ged_lsape_batch: strides too small");
     if (max_n1 + max_n2 > 448) return fail(GED_E_TOO_LARGE, "n1+n2 above 448 is not supported by this build");
-    LsapeParams prm{B, n1, n2, cost, (long long)mat_stride, rowmatch, colmatch, ms1, ms2, lb, status, make_layout(max_n1, max_n2)};
-    const int S = slots_for(max_n1, max_n2);
-    GED_DISPATCH_S(S, ged_lsape_kernel, prm, B, prm.layout.bytes, (cudaStream_t)stream, "ged_lsape_batch")
+    LsapeParams prm{B, n1, n2, cost, (long long)mat_stride, rowmatch, colmatch, ms1, ms2, lb, status, max_n1, max_n2, make_layout(max_n1, max_n2)};
+    return dispatch_lsape(slots_for(max_n1, max_n2), prm, (cudaStream_t)stream);
 }
 
-int ged_kv_batch(const ged_pairs *pairs, const float *x, float *cost, int64_t mat_stride, void *stream)
+int ged_kv_batch(const ged_pairs *pairs, const float *x, float *cost, float *scratch, int64_t mat_stride, void *stream)
 {
-    if (!pairs || !x || !cost) return fail(GED_E_BADARG, "ged_kv_batch: null pointer");
+    if (!pairs || !x || !cost || !scratch) return fail(GED_E_BADARG, "ged_kv_batch: null pointer");
     if (int rc = check_pairs(*pairs)) return rc;
     if (pairs->num_pairs == 0) return GED_OK;
     if (mat_stride < (int64_t)(pairs->max_n1 + 1) * (pairs->max_n2 + 1)) return fail(GED_E_BADARG, "ged_kv_batch: mat_stride too small");
-    KvParams prm{*pairs, x, cost, (long long)mat_stride, make_layout(pairs->max_n1, pairs->max_n2)};
-    const int S = slots_for(pairs->max_n1, pairs->max_n2);
-    GED_DISPATCH_S(S, ged_kv_kernel, prm, pairs->num_pairs, prm.layout.bytes, (cudaStream_t)stream, "ged_kv_batch")
+    KvParams prm{*pairs, x, cost, scratch, (long long)mat_stride, make_layout(pairs->max_n1, pairs->max_n2)};
+    return dispatch_kv(slots_for(pairs->max_n1, pairs->max_n2), prm, (cudaStream_t)stream);
 }
 
 int ged_score_batch(const ged_pairs *pairs, int32_t B, const int32_t *base_idx, const int32_t *rowmatch, int32_t ms1,
@@ -1283,8 +1480,7 @@ int ged_score_batch(const ged_pairs *pairs, int32_t B, const int32_t *base_idx, 
     if (!base_idx && B != pairs->num_pairs) return fail(GED_E_BADARG, "ged_score_batch: B != num_pairs without base_idx");
     if (ms1 < pairs->max_n1 || ms2 < pairs->max_n2) return fail(GED_E_BADARG, "ged_score_batch: match strides too small");
     ScoreParams prm{*pairs, B, base_idx, rowmatch, colmatch, ms1, ms2, ged, make_layout(pairs->max_n1, pairs->max_n2)};
-    const int S = slots_for(pairs->max_n1, pairs->max_n2);
-    GED_DISPATCH_S(S, ged_score_kernel, prm, B, prm.layout.bytes, (cudaStream_t)stream, "ged_score_batch")
+    return launch_uniform(ged_score_kernel, prm, B, prm.layout.bytes, (cudaStream_t)stream, "ged_score_batch");
 }
 
 static int quadform_rows_per_cta(int B, int nk)
@@ -1325,17 +1521,25 @@ void ged_limits(int32_t *max_nodes_per_graph, int32_t *max_matrix_elems)
 {
     if (max_nodes_per_graph) *max_nodes_per_graph = 32 * kMaxS;
     if (max_matrix_elems) {
-        // largest square pair whose slice fits
-        int n = 1;
-        while (make_layout(n + 1, n + 1).bytes <= kMaxSmemBytes) ++n;
+        int n = 1;                          // largest square pair whose shared-memory-backed slice fits
+        for (;;) {
+            const SliceLayout L = make_layout(n + 1, n + 1);
+            if (L.bytes + L.cost_bytes > kMaxSmemBytes) break;
+            ++n;
+        }
         *max_matrix_elems = (n + 1) * (n + 1);
     }
 }
 
-int64_t ged_solve_smem_bytes(int32_t max_n1, int32_t max_n2) { return make_layout(max_n1, max_n2).bytes; }
+int64_t ged_solve_smem_bytes(int32_t max_n1, int32_t max_n2)
+{
+    const SliceLayout L = make_layout(max_n1, max_n2);
+    return L.bytes + L.cost_bytes;
+}
 
 int ged_abi_version(void) { return GED_ABI_VERSION; }
-const char *ged_version(void) { return "ged_b200 0.1.0 (sm_100a; canonical order v1)"; }
+const char *ged_version(void) { return "ged_b200 0.3.0 (sm_100a; canonical order v2; tensor-memory cost store)"; }
 const char *ged_last_error(void) { return g_err; }
 
 }  // extern "C"
+#endif  // !GED_TU_S

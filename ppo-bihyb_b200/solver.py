@@ -219,10 +219,13 @@ def kv_batch(pairs: PairSet, x: torch.Tensor) -> torch.Tensor:
     x = x.to(device=dev, dtype=torch.float32).reshape(pairs.num_pairs, -1).contiguous()
     ms = x.shape[1]
     out = torch.zeros_like(x)
+    scratch = torch.empty_like(x)
     p = _lib.ptr
     cs = pairs.c_struct()
     with torch.cuda.device(dev):
-        _lib.check(lib.ged_kv_batch(cs, p(x, _lib.c_f32p), p(out, _lib.c_f32p), ms, _stream(dev)), "ged_kv_batch")
+        _lib.check(lib.ged_kv_batch(cs, p(x, _lib.c_f32p), p(out, _lib.c_f32p), p(scratch, _lib.c_f32p), ms, _stream(dev)),
+                   "ged_kv_batch")
+    scratch.record_stream(torch.cuda.current_stream(dev))
     return out
 
 

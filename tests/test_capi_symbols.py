@@ -69,4 +69,4 @@ def test_bad_arguments_are_reported_not_crashed():
     assert lib.ged_lsape_batch(-1, None, None, 1, 1, None, 4, None, 1, None, 1, None, None, None) == _lib.GED_E_BADARG
     pairs = _lib.GedPairs()
     pairs.num_pairs, pairs.max_n1, pairs.max_n2 = 1, 300, 300
-    assert lib.ged_kv_batch(ctypes.byref(pairs), ctypes.cast(8, _lib.c_f32p), ctypes.cast(8, _lib.c_f32p), 1 << 20, None) != _lib.GED_OK
+    assert lib.ged_kv_batch(ctypes.byref(pairs), ctypes.cast(8, _lib.c_f32p), ctypes.cast(8, _lib.c_f32p), ctypes.cast(8, _lib.c_f32p), 1 << 20, None) != _lib.GED_OK
