@@ -87,7 +87,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = args.cpu_sample or max(threads, min(256, 4 * threads))
+    sample = args.cpu_sample or max(128, 8 * threads)
     for _ in range(min(args.warmup, 1)):
         cpu_baseline(args, max(threads, 8), threads)
     vals, dts = [], []
@@ -292,7 +292,7 @@ def main():
         }
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            sample = args.cpu_sample or max(threads, min(128, 2 * threads))
+            sample = args.cpu_sample or max(128, 8 * threads)
             v, dt, idx, geds = cpu_baseline(args, sample, threads)
             same = bool(np.array_equal(np.asarray(geds, np.float32), res.ged.cpu().numpy()[idx]))
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",

@@ -1301,11 +1301,13 @@ static CtaShape plan_cta(const SliceLayout &L, int max_n1, int S, int regs_per_t
         const int budget = kMaxSmemBytes / q - 1024;           // shared memory per CTA (static + reserved included)
         int k = (budget - kTmemWarps * L.bytes) / big;
         if (budget < kTmemWarps * L.bytes) k = -1;
-        if (mode == 1 && k > 0) k = 0;
+        // measured on B200 (profiles/): the solve is close to issue-bound once ~8-16 warps per SM are in flight, so extra
+        // shared-memory-backed warps only pay when tensor memory can serve a single CTA per SM (n1 * S > 256 columns)
+        if ((mode == 1 || q >= 2) && k > 0) k = 0;
         const int kmax = max_warps_by_regs / q - kTmemWarps;
         if (k > kmax) k = kmax;
         const int kforce = env_int("GED_B200_SMEM_WARPS", -1);
-        if (kforce >= 0 && kforce <= k) k = kforce;
+        if (kforce >= 0) { k = (budget - kTmemWarps * L.bytes) / big; if (k > kmax) k = kmax; if (kforce < k) k = kforce; }
         if (k >= 0) {
             c.tmem_warps = kTmemWarps;
             c.tmem_cols = cols;
