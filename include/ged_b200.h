@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GED_ABI_VERSION 3
+#define GED_ABI_VERSION 4
 
 /* call-level errors */
 #define GED_OK 0
@@ -77,7 +77,16 @@ typedef struct ged_solve_desc {
     const float *x_init;
     int64_t mat_stride;      /* elements between consecutive candidates in x_init / x_out / workspace / trace;
                                 must be >= (max_n1+1)*(max_n2+1) */
-    float *workspace;        /* 2 * B * mat_stride floats of scratch: per candidate the fractional iterate X and X*A2^T (L2 resident) */
+    /* Scratch for the fractional iterate X and X*A2^T of the solves in flight (touched only between LAPs, L2 resident):
+     * `workspace_slots` rows of 2 * workspace_stride floats.  A solve claims a free row for its lifetime with an atomic
+     * compare-and-swap on workspace_locks[row] (int32, zero-initialised by the caller, zero again when the launch ends),
+     * so the footprint follows the solves RESIDENT on the device (ged_solve_max_resident), not the batch size.
+     * workspace_slots == 0: legacy layout, row b belongs to candidate b (B rows, no locks).
+     * workspace_stride == 0 means mat_stride; it must be >= (max_n1+1)*(max_n2+1). */
+    float *workspace;
+    int32_t *workspace_locks;
+    int32_t workspace_slots;
+    int64_t workspace_stride;
     /* Optional sub-launch: solve only candidates order[0 .. order_count) (indices into the B candidates; results are
      * still written at the candidate's own index).  The host layer uses this to launch one size class at a time with
      * that class's max_n1/max_n2, so that shared memory per solve follows the pair's size, not the batch maximum. */
@@ -138,6 +147,10 @@ int ged_quadform_dense_batch(int32_t B, int32_t nk, const float *k, int64_t k_st
 
 /* Size limits of this build: largest n1+n2 and largest (n1+1)*(n2+1) a single warp's shared-memory slice holds. */
 void ged_limits(int32_t *max_nodes_per_graph, int32_t *max_matrix_elems);
+
+/* Upper bound on the solves of one ged_solve_batch launch that can be resident on the current device at once for the
+ * given size bounds (SM count x CTAs per SM x warps per CTA of the launch shape): enough workspace rows for a launch. */
+int32_t ged_solve_max_resident(int32_t max_n1, int32_t max_n2);
 
 /* Bytes of dynamic shared memory one solve uses for the given bounds (diagnostics / occupancy planning). */
 int64_t ged_solve_smem_bytes(int32_t max_n1, int32_t max_n2);

@@ -19,12 +19,12 @@ c_u64p = ctypes.POINTER(ctypes.c_ulonglong)
 GED_OK, GED_E_BADARG, GED_E_TOO_LARGE, GED_E_CUDA = 0, 1, 2, 3
 GED_ST_INVALID_COST, GED_ST_INFEASIBLE, GED_ST_BAD_GRAPH = 1, 2, 4
 GED_SOLVER_IPFP, GED_SOLVER_HUNGARIAN = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # every symbol include/ged_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED_SYMBOLS = (
     "ged_solve_batch", "ged_lsape_batch", "ged_kv_batch", "ged_score_batch", "ged_quadform_ws_elems",
-    "ged_quadform_dense_batch", "ged_limits", "ged_solve_smem_bytes", "ged_abi_version", "ged_version",
+    "ged_quadform_dense_batch", "ged_limits", "ged_solve_smem_bytes", "ged_solve_max_resident", "ged_abi_version", "ged_version",
     "ged_last_error",
 )
 
@@ -54,6 +54,9 @@ class GedSolveDesc(ctypes.Structure):
         ("x_init", c_f32p),
         ("mat_stride", ctypes.c_int64),
         ("workspace", c_f32p),
+        ("workspace_locks", c_i32p),
+        ("workspace_slots", ctypes.c_int32),
+        ("workspace_stride", ctypes.c_int64),
         ("order", c_i32p),
         ("order_count", ctypes.c_int32),
     ]
@@ -108,6 +111,8 @@ def load():
     lib.ged_quadform_dense_batch.restype = ctypes.c_int
     lib.ged_limits.argtypes = [c_i32p, c_i32p]
     lib.ged_limits.restype = None
+    lib.ged_solve_max_resident.argtypes = [ctypes.c_int32, ctypes.c_int32]
+    lib.ged_solve_max_resident.restype = ctypes.c_int32
     lib.ged_solve_smem_bytes.argtypes = [ctypes.c_int32, ctypes.c_int32]
     lib.ged_solve_smem_bytes.restype = ctypes.c_int64
     lib.ged_abi_version.restype = ctypes.c_int

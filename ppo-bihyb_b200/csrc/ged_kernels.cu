@@ -260,18 +260,27 @@ __device__ __forceinline__ double double_from_ord(unsigned ohi, unsigned olo)
 // ---- per-slot building blocks of the LAP scan step, written as PTX so that each is exactly the intended handful of
 // SASS instructions (LOP3 -> predicate, DSETP with the predicate folded in, selects) without moves or branches -----------
 
-// if (live & MASK) && r < spc:  spc = r, pth = i, improved = 1
-template <unsigned MASK>
+// if (live & MASK) && r < spc:  spc = r, pth = i (and, when TRACK, improved = 1)
+template <unsigned MASK, bool TRACK = true>
 __device__ __forceinline__ void lap_relax(double &spc, int &pth, int &improved, double r, int i, unsigned live)
 {
-    asm("{\n\t.reg .pred q, p;\n\t.reg .b32 t;\n\t"
-        "and.b32 t, %5, %6;\n\t"
-        "setp.ne.u32 q, t, 0;\n\t"
-        "setp.lt.and.f64 p, %3, %0, q;\n\t"
-        "selp.f64 %0, %3, %0, p;\n\t"
-        "selp.b32 %1, %4, %1, p;\n\t"
-        "@p mov.b32 %2, 1;\n\t}"
-        : "+d"(spc), "+r"(pth), "+r"(improved) : "d"(r), "r"(i), "r"(live), "n"(MASK));
+    if constexpr (TRACK)
+        asm("{\n\t.reg .pred q, p;\n\t.reg .b32 t;\n\t"
+            "and.b32 t, %5, %6;\n\t"
+            "setp.ne.u32 q, t, 0;\n\t"
+            "setp.lt.and.f64 p, %3, %0, q;\n\t"
+            "selp.f64 %0, %3, %0, p;\n\t"
+            "selp.b32 %1, %4, %1, p;\n\t"
+            "@p mov.b32 %2, 1;\n\t}"
+            : "+d"(spc), "+r"(pth), "+r"(improved) : "d"(r), "r"(i), "r"(live), "n"(MASK));
+    else
+        asm("{\n\t.reg .pred q, p;\n\t.reg .b32 t;\n\t"
+            "and.b32 t, %4, %5;\n\t"
+            "setp.ne.u32 q, t, 0;\n\t"
+            "setp.lt.and.f64 p, %2, %0, q;\n\t"
+            "selp.f64 %0, %2, %0, p;\n\t"
+            "selp.b32 %1, %3, %1, p;\n\t}"
+            : "+d"(spc), "+r"(pth) : "d"(r), "r"(i), "r"(live), "n"(MASK));
 }
 // if (live & MASK) && spc < lm:  lm = spc
 template <unsigned MASK>
@@ -301,13 +310,32 @@ __device__ __forceinline__ void lap_min_key(unsigned &lk, double spc, double min
 template <int S, int I = 0>
 struct LapSlots {
     // slots [LO, HI): relax with r = base - v[slot]
-    template <int LO, int HI>
+    template <int LO, int HI, bool TRACK = true>
     static __device__ __forceinline__ void relax_base(double (&spc)[2 * S], int (&pth)[2 * S], int &improved,
                                                       const double (&v)[2 * S], double base, int i, unsigned live)
     {
         if constexpr (I < 2 * S) {
-            if constexpr (I >= LO && I < HI) lap_relax<(1u << I)>(spc[I], pth[I], improved, __dsub_rn(base, v[I]), i, live);
-            LapSlots<S, I + 1>::template relax_base<LO, HI>(spc, pth, improved, v, base, i, live);
+            if constexpr (I >= LO && I < HI)
+                lap_relax<(1u << I), TRACK>(spc[I], pth[I], improved, __dsub_rn(base, v[I]), i, live);
+            LapSlots<S, I + 1>::template relax_base<LO, HI, TRACK>(spc, pth, improved, v, base, i, live);
+        }
+    }
+    // exactly one slot of [LO, HI) -- slot LO + sel, sel warp-uniform -- is relaxed (the row's own deletion / insertion
+    // entry).  Up to two slots per group it is cheaper to run all of them under a lane mask; above that, branch.
+    template <int LO, int HI, bool TRACK = true>
+    static __device__ __forceinline__ void relax_one(double (&spc)[2 * S], int (&pth)[2 * S], int &improved,
+                                                     const double (&v)[2 * S], double base, int i, unsigned live_lane, int sel)
+    {
+        if constexpr (S <= 2) {
+            relax_base<LO, HI, TRACK>(spc, pth, improved, v, base, i, live_lane & ((1u << LO) << sel));
+        } else if constexpr (I < 2 * S) {
+            if constexpr (I >= LO && I < HI) {
+                if (sel == I - LO) {
+                    lap_relax<(1u << I), TRACK>(spc[I], pth[I], improved, __dsub_rn(base, v[I]), i, live_lane);
+                    return;
+                }
+            }
+            LapSlots<S, I + 1>::template relax_one<LO, HI, TRACK>(spc, pth, improved, v, base, i, live_lane, sel);
         }
     }
     // real slots [0, S): relax with SciPy's r = ((minVal + c) - u[i]) - v[j]
@@ -317,7 +345,7 @@ struct LapSlots {
     {
         if constexpr (I < S) {
             const double r = __dsub_rn(__dsub_rn(__dadd_rn(minVal, (double)cs[I]), ui), v[I]);
-            lap_relax<(1u << I)>(spc[I], pth[I], improved, r, i, live);
+            lap_relax<(1u << I), false>(spc[I], pth[I], improved, r, i, live);
             LapSlots<S, I + 1>::relax_row(spc, pth, improved, v, cs, minVal, ui, i, live);
         }
     }
@@ -410,14 +438,12 @@ __device__ int lsape_warp(const Store &store, bool invalid, int n1, int n2, cons
                 if (!Store::kPrefetch) store.row(i, cs);
                 LapSlots<S>::relax_row(spc, pth, improved, v, cs, minVal, ui, i, live);
                 const double rd = __dsub_rn(__dadd_rn(minVal, (double)cx), ui);
-                const unsigned hl = (lane == (i & 31)) ? (live & ((1u << S) << (i >> 5))) : 0u;
-                LapSlots<S>::template relax_base<S, 2 * S>(spc, pth, improved, v, rd, i, hl);
+                LapSlots<S>::template relax_one<S, 2 * S, false>(spc, pth, improved, v, rd, i, (lane == (i & 31)) ? live : 0u, i >> 5);
                 // a real row almost always lowers something: recompute the minimum right away
             } else {                         // insertion row of column a0: its own entry + the zero block
                 const int a0 = i - n1;
                 const double ra = __dsub_rn(__dadd_rn(minVal, (double)cx), ui);
-                const unsigned hl = (lane == (a0 & 31)) ? (live & (1u << (a0 >> 5))) : 0u;
-                LapSlots<S>::template relax_base<0, S>(spc, pth, improved, v, ra, i, hl);
+                LapSlots<S>::template relax_one<0, S>(spc, pth, improved, v, ra, i, (lane == (a0 & 31)) ? live : 0u, a0 >> 5);
                 // zero block: r = rz - v[j].  Rounding is monotone in rz, and after a scan with value rz0 every remaining
                 // deletion column has spc <= fl(rz0 - v[j]); a later insertion row with rz >= rz0 cannot lower any of them.
                 const double rz = __dsub_rn(__dadd_rn(minVal, 0.0), ui);
@@ -830,6 +856,9 @@ struct SolveParams {
     const float *x_init;
     long long mat_stride;
     float *workspace;
+    int32_t *ws_locks;
+    int ws_slots;
+    long long ws_stride;
     const int32_t *order;
     int count;
     int tmem_warps;          // 0 or 4: warps 0..3 of every CTA keep their cost matrix in tensor memory
@@ -863,7 +892,7 @@ __device__ inline void load_pair(const ged_pairs &pp, int p, const Slice &sm, Pa
 
 // One candidate solve by one warp: GEDenv.step :110-124 -> solve_feasible_ged :140-158 -> ipfp_ged :256-289.
 template <int S, class Store>
-__device__ void solve_one(const SolveParams &prm, int b, const Slice &sm, const Store &store)
+__device__ void solve_one(const SolveParams &prm, int b, int slot, const Slice &sm, const Store &store)
 {
     const int lane = threadIdx.x & 31;
     const ged_solve_out &out = prm.out;
@@ -892,8 +921,18 @@ __device__ void solve_one(const SolveParams &prm, int b, const Slice &sm, const 
     }
     const int nnz1 = count_bits(sm.bits1, P.R * P.W1), nnz2 = count_bits(sm.bits2, P.C * P.W2);
 
-    float *X = prm.workspace ? prm.workspace + (long long)b * 2 * prm.mat_stride : nullptr;   // fractional iterate
-    float *Y = X ? X + prm.mat_stride : nullptr;                                              // X A2^T scratch of kv_apply
+    // scratch row for the fractional iterate X and Y = X A2^T: claimed among the rows of the solves in flight
+    int ws_row = b;
+    if (prm.workspace && prm.ws_slots > 0) {
+        if (lane == 0) {
+            int h = slot % prm.ws_slots;
+            while (atomicCAS(prm.ws_locks + h, 0, 1) != 0) h = (h + 1 == prm.ws_slots) ? 0 : h + 1;
+            ws_row = h;
+        }
+        ws_row = __shfl_sync(kFull, ws_row, 0);
+    }
+    float *X = prm.workspace ? prm.workspace + (long long)ws_row * 2 * prm.ws_stride : nullptr;
+    float *Y = X ? X + prm.ws_stride : nullptr;
     unsigned long long lap_steps = 0;
     int iters = 0;
     double best_ub = INFINITY;
@@ -1025,6 +1064,10 @@ __device__ void solve_one(const SolveParams &prm, int b, const Slice &sm, const 
         if (out.status) out.status[b] = status;
         if (out.tr_lap_steps) out.tr_lap_steps[b] = lap_steps;
     }
+    if (prm.workspace && prm.ws_slots > 0) {     // release the scratch row (all of this warp's accesses to it are done)
+        __syncwarp();
+        if (lane == 0) { __threadfence(); atomicExch(prm.ws_locks + ws_row, 0); }
+    }
     if (status == 0) {
         for (int i = lane; i < n1; i += 32) out.rowmatch[(long long)b * out.match_stride_1 + i] = sm.bestrow[i];
         for (int a = lane; a < n2; a += 32) out.colmatch[(long long)b * out.match_stride_2 + a] = sm.bestcol[a];
@@ -1068,7 +1111,7 @@ __global__ void ged_solve_kernel(SolveParams prm)
             if (warp < nt) {
                 const Slice sm = carve(smem_raw + (size_t)warp * prm.layout.bytes, prm.layout, m1, m2, false);
                 TmemCost<S> store{tmem_base + ((uint32_t)(32 * warp) << 16)};
-                solve_one<S>(prm, b, sm, store);
+                solve_one<S>(prm, b, slot, sm, store);
                 done = true;
             }
         }
@@ -1076,7 +1119,7 @@ __global__ void ged_solve_kernel(SolveParams prm)
             unsigned char *base = smem_raw + (size_t)nt * prm.layout.bytes + (size_t)(warp - nt) * (prm.layout.bytes + prm.layout.cost_bytes);
             const Slice sm = carve(base, prm.layout, m1, m2, true);
             SmemCost<S> store{sm.cost, prm.pairs.n2[prm.base_idx ? prm.base_idx[b] : b]};
-            solve_one<S>(prm, b, sm, store);
+            solve_one<S>(prm, b, slot, sm, store);
         }
     }
     if constexpr (TM) {
@@ -1354,6 +1397,7 @@ int launch_solve(const SolveParams &prm, cudaStream_t stream)
 #define GED_CAT_(a, b) a##b
 #define GED_CAT(a, b) GED_CAT_(a, b)
 #define GED_DECLARE_S(k)                                                  \
+    int GED_CAT(resident_solve_s, k)(const SliceLayout &, int);           \
     int GED_CAT(launch_solve_s, k)(const SolveParams &, cudaStream_t);    \
     int GED_CAT(launch_lsape_s, k)(const LsapeParams &, cudaStream_t);    \
     int GED_CAT(launch_kv_s, k)(const KvParams &, cudaStream_t);
@@ -1361,6 +1405,19 @@ GED_DECLARE_S(1) GED_DECLARE_S(2) GED_DECLARE_S(3) GED_DECLARE_S(4) GED_DECLARE_
 
 #ifdef GED_TU_S
 int GED_CAT(launch_solve_s, GED_TU_S)(const SolveParams &prm, cudaStream_t stream) { return launch_solve<GED_TU_S>(prm, stream); }
+// solves of one launch that fit one SM at once (CTAs per SM by tensor-memory columns / shared memory / registers x warps per CTA)
+int GED_CAT(resident_solve_s, GED_TU_S)(const SliceLayout &L, int max_n1)
+{
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, ged_solve_kernel<GED_TU_S, true>) != cudaSuccess) return -1;
+    const CtaShape c = plan_cta(L, max_n1, GED_TU_S, fa.numRegs);
+    const int wpb = c.tmem_warps + c.smem_warps;
+    int ctas = 32;
+    if (c.smem_bytes > 0) ctas = min(ctas, kMaxSmemBytes / c.smem_bytes);
+    if (c.tmem_cols > 0) ctas = min(ctas, 512 / c.tmem_cols);
+    ctas = min(ctas, 64 / wpb);
+    return (ctas < 1 ? 1 : ctas) * wpb;
+}
 int GED_CAT(launch_lsape_s, GED_TU_S)(const LsapeParams &prm, cudaStream_t stream)
 {
     return launch_uniform(ged_lsape_kernel<GED_TU_S>, prm, prm.B, prm.layout.bytes + prm.layout.cost_bytes, stream, "ged_lsape_batch");
@@ -1399,6 +1456,7 @@ static int check_pairs(const ged_pairs &p)
 static int dispatch_solve(int S, const SolveParams &prm, cudaStream_t stream) { GED_DISPATCH_S(S, launch_solve_s, prm, stream) }
 static int dispatch_lsape(int S, const LsapeParams &prm, cudaStream_t stream) { GED_DISPATCH_S(S, launch_lsape_s, prm, stream) }
 static int dispatch_kv(int S, const KvParams &prm, cudaStream_t stream) { GED_DISPATCH_S(S, launch_kv_s, prm, stream) }
+static int dispatch_resident(int S, const SliceLayout &L, int max_n1) { GED_DISPATCH_S(S, resident_solve_s, L, max_n1) }
 #endif  // GED_TU_S
 
 }  // namespace ged_impl
@@ -1438,6 +1496,11 @@ int ged_solve_batch(const ged_solve_desc *d, const ged_solve_out *o, void *strea
     prm.x_init = d->x_init;
     prm.mat_stride = d->mat_stride;
     prm.workspace = d->workspace;
+    prm.ws_locks = d->workspace_locks;
+    prm.ws_slots = d->workspace_slots;
+    prm.ws_stride = d->workspace_stride ? d->workspace_stride : d->mat_stride;
+    if (prm.ws_slots < 0 || (prm.ws_slots > 0 && !prm.ws_locks)) return fail(GED_E_BADARG, "ged_solve_batch: workspace_slots needs workspace_locks");
+    if (prm.ws_stride < need) return fail(GED_E_BADARG, "ged_solve_batch: workspace_stride < (max_n1+1)*(max_n2+1)");
     prm.order = d->order;
     prm.count = d->order ? d->order_count : d->B;
     if (prm.count < 0 || prm.count > d->B) return fail(GED_E_BADARG, "ged_solve_batch: order_count out of range");
@@ -1531,6 +1594,15 @@ void ged_limits(int32_t *max_nodes_per_graph, int32_t *max_matrix_elems)
         }
         *max_matrix_elems = (n + 1) * (n + 1);
     }
+}
+
+int32_t ged_solve_max_resident(int32_t max_n1, int32_t max_n2)
+{
+    if (max_n1 < 1 || max_n2 < 1 || max_n1 + max_n2 > 448) return 0;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    const int per_sm = dispatch_resident(slots_for(max_n1, max_n2), make_layout(max_n1, max_n2), max_n1);
+    return per_sm > 0 ? per_sm * sms : 0;
 }
 
 int64_t ged_solve_smem_bytes(int32_t max_n1, int32_t max_n2)

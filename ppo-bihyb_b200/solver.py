@@ -113,7 +113,21 @@ def solve_batch(pairs: PairSet, base_idx=None, edit_u=None, edit_v=None, solver:
     res = SolveResult(ged=torch.empty(B, **f32), ged_edited=torch.empty(B, **f32),
                       rowmatch=torch.empty(B, m1, **i32), colmatch=torch.empty(B, m2, **i32),
                       iters=torch.empty(B, **i32), status=torch.empty(B, **i32))
-    workspace = torch.empty(2 * B * ms, **f32) if solver == "ipfp" else None
+    # Scratch rows for the solves in flight (the iterate X and X*A2^T): one region per launch, sized by the number of
+    # solves the device can hold at once, claimed row by row inside the kernel (ged_solve_desc.workspace_*).
+    launches = [(0, B, m1, m2)] if (plan is None or len(plan[1]) <= 1) else list(plan[1])
+    regions, workspace, locks = [], None, None
+    if solver == "ipfp" or x_init is not None:
+        with torch.cuda.device(dev):
+            floats = rows = 0
+            for (_, count, c1, c2) in launches:
+                slots = max(1, min(count, int(lib.ged_solve_max_resident(c1, c2))))
+                stride = (c1 + 1) * (c2 + 1)
+                regions.append((floats, rows, slots, stride))
+                floats += 2 * slots * stride
+                rows += slots
+        workspace = torch.empty(floats, **f32)
+        locks = torch.zeros(rows, **i32)
     if x_init is not None:
         x_init = x_init.to(**f32).contiguous()
         assert x_init.numel() == B * ms, "x_init must be [B, mat_stride]"
@@ -131,7 +145,15 @@ def solve_batch(pairs: PairSet, base_idx=None, edit_u=None, edit_v=None, solver:
     desc = _lib.GedSolveDesc(pairs.c_struct(), B, p(base_idx, _lib.c_i32p), p(edit_u, _lib.c_i32p), p(edit_v, _lib.c_i32p),
                              p(score_adj1, _lib.c_u8p), p(score_adj1_off, _lib.c_i64p), p(score_idx, _lib.c_i32p),
                              int(max_iter), SOLVERS[solver], p(x_init, _lib.c_f32p), ms, p(workspace, _lib.c_f32p),
-                             p(None, _lib.c_i32p), 0)
+                             p(locks, _lib.c_i32p), 0, 0, p(None, _lib.c_i32p), 0)
+
+    def set_region(k):
+        if regions:
+            f_off, r_off, slots, stride = regions[k]
+            desc.workspace = ctypes.cast(ctypes.c_void_p(workspace.data_ptr() + 4 * f_off), _lib.c_f32p)
+            desc.workspace_locks = ctypes.cast(ctypes.c_void_p(locks.data_ptr() + 4 * r_off), _lib.c_i32p)
+            desc.workspace_slots, desc.workspace_stride = slots, stride
+
     out = _lib.GedSolveOut(p(res.ged, _lib.c_f32p), p(res.ged_edited, _lib.c_f32p), p(res.rowmatch, _lib.c_i32p),
                            p(res.colmatch, _lib.c_i32p), m1, m2, p(res.iters, _lib.c_i32p), p(res.status, _lib.c_i32p),
                            p(res.x, _lib.c_f32p),
@@ -141,6 +163,7 @@ def solve_batch(pairs: PairSet, base_idx=None, edit_u=None, edit_v=None, solver:
                            p(tr.get("init_colmatch"), _lib.c_i32p), p(tr.get("lap_steps"), _lib.c_u64p))
     with torch.cuda.device(dev):
         if plan is None or len(plan[1]) <= 1:
+            set_region(0)
             _lib.check(lib.ged_solve_batch(desc, out, _stream(dev)), "ged_solve_batch")
             res.launches = 1
         else:
@@ -149,8 +172,9 @@ def solve_batch(pairs: PairSet, base_idx=None, edit_u=None, edit_v=None, solver:
             streams = _streams(dev, len(classes))
             ready = torch.cuda.Event()
             ready.record(cur)
-            for (off, count, c1, c2), st in zip(classes, streams):
+            for k, ((off, count, c1, c2), st) in enumerate(zip(classes, streams)):
                 st.wait_event(ready)
+                set_region(k)
                 desc.pairs.max_n1, desc.pairs.max_n2 = c1, c2
                 desc.order = ctypes.cast(ctypes.c_void_p(order_dev.data_ptr() + 4 * off), _lib.c_i32p)
                 desc.order_count = count
@@ -161,6 +185,7 @@ def solve_batch(pairs: PairSet, base_idx=None, edit_u=None, edit_v=None, solver:
             res.launches = len(classes)
     if workspace is not None:
         workspace.record_stream(torch.cuda.current_stream(dev))
+        locks.record_stream(torch.cuda.current_stream(dev))
     if check:
         res.raise_on_error()
     return res

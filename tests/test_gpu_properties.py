@@ -1,0 +1,104 @@
+"""GPU: size-independent properties at BASELINE.json's full sizes (where the oracle is too slow to check every solve),
+plus the launch-shape variants of the solve kernel (tensor-memory / shared-memory / hybrid cost store, scratch-row
+recycling, size classes), which must all return bit-identical results."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ged_oracle as go
+from ppo_bihyb_b200 import solver, synthetic
+from ppo_bihyb_b200.graphs import PairSet, label_node_cost
+
+pytestmark = pytest.mark.gpu
+
+
+def _solve(ps, edits, **kw):
+    return solver.solve_batch(ps, base_idx=edits[0], edit_u=edits[1], edit_v=edits[2], check=True, **kw)
+
+
+def test_full_size_batch_properties(cuda_device):
+    """AIDS-50+ shape, 2048 candidates: every returned assignment is a valid LSAPE solution whose objective (re-scored by
+    the stand-alone scoring kernel) equals the reported one; IPFP never ends worse than its Hungarian start; a sample is
+    checked against the oracle; the run is deterministic."""
+    pairs = synthetic.make_pairs("aids-50+", 32, seed_offset=51)
+    edits = synthetic.make_edits(pairs, 64, seed_offset=51)
+    ps = PairSet.from_host(pairs, cuda_device)
+    res = _solve(ps, edits)
+    again = _solve(ps, edits)
+    assert torch.equal(res.ged, again.ged) and torch.equal(res.rowmatch, again.rowmatch) and torch.equal(res.iters, again.iters)
+    hun = _solve(ps, edits, solver="hungarian")
+    assert bool((res.ged_edited <= hun.ged_edited).all())
+    rescored = solver.score_batch(ps, res.rowmatch, res.colmatch, base_idx=edits[0])
+    assert torch.equal(rescored, res.ged)
+    rm, cm = res.rowmatch.cpu().numpy(), res.colmatch.cpu().numpy()
+    n1 = np.asarray([pairs[p][0].n for p in edits[0]])
+    n2 = np.asarray([pairs[p][1].n for p in edits[0]])
+    for b in range(0, len(n1), 37):
+        r, c = rm[b, :n1[b]], cm[b, :n2[b]]
+        used = r[r < n2[b]]
+        assert len(np.unique(used)) == len(used)                       # injective on the substituted rows
+        assert np.all((c == n1[b]) == ~np.isin(np.arange(n2[b]), used))  # unmatched columns are exactly the inserted ones
+        assert np.all(r[c[c < n1[b]]] == np.nonzero(c < n1[b])[0])     # row/column views agree
+    ged = res.ged.cpu().numpy()
+    for b in (0, 777, 2047):
+        g1, g2 = pairs[edits[0][b]]
+        o = go.solve(g1.adj, g2.adj, label_node_cost(g1.labels, g2.labels), edit=(int(edits[1][b]), int(edits[2][b])))
+        assert ged[b] == o["ged"] and np.array_equal(rm[b, :g1.n], o["rowmatch"]) and int(res.iters[b]) == o["iters"]
+
+
+@pytest.mark.parametrize("config,num,per", [("aids-30-50", 8, 24), ("n=70", 3, 8), ("n=100", 2, 6)])
+def test_cost_store_variants_are_bit_identical(cuda_device, config, num, per, monkeypatch):
+    """Tensor-memory, shared-memory and hybrid launches of the same batch (incl. a size whose matrix needs the hybrid
+    CTA and one that needs S=4 slots) give the same bits; one candidate per size is checked against the oracle."""
+    pairs = synthetic.make_pairs(config, num, seed_offset=61)
+    edits = synthetic.make_edits(pairs, per, seed_offset=61)
+    ps = PairSet.from_host(pairs, cuda_device)
+    outs = []
+    for mode in ("0", "1", "2"):
+        monkeypatch.setenv("GED_B200_COST_STORE", mode)
+        if mode == "2":
+            monkeypatch.setenv("GED_B200_SMEM_WARPS", "2")            # force shared-memory warps into the hybrid CTA
+        outs.append(_solve(ps, edits))
+    for o in outs[1:]:
+        assert torch.equal(o.ged, outs[0].ged) and torch.equal(o.rowmatch, outs[0].rowmatch)
+        assert torch.equal(o.colmatch, outs[0].colmatch) and torch.equal(o.iters, outs[0].iters)
+    g1, g2 = pairs[edits[0][1]]
+    o = go.solve(g1.adj, g2.adj, label_node_cost(g1.labels, g2.labels), edit=(int(edits[1][1]), int(edits[2][1])))
+    assert float(outs[0].ged[1]) == o["ged"] and int(outs[0].iters[1]) == o["iters"]
+    assert np.array_equal(outs[0].rowmatch[1, :g1.n].cpu().numpy(), o["rowmatch"])
+
+
+def test_scratch_rows_are_recycled_without_interference(cuda_device):
+    """More candidates than the device can hold at once: scratch rows are claimed and released by the solves in flight.
+    The result must equal the one-launch-per-candidate-subset result (which uses disjoint rows)."""
+    pairs = synthetic.make_pairs("aids-20-30", 16, seed_offset=71)
+    edits = synthetic.make_edits(pairs, 640, seed_offset=71)                # 10240 candidates
+    ps = PairSet.from_host(pairs, cuda_device)
+    full = _solve(ps, edits)
+    with torch.cuda.device(cuda_device):
+        resident = solver._lib.load().ged_solve_max_resident(ps.max_n1, ps.max_n2)
+    assert 0 < resident < len(edits[0])
+    part = [_solve(ps, tuple(e[lo:lo + 1024] for e in edits)) for lo in range(0, len(edits[0]), 1024)]
+    assert torch.equal(full.ged, torch.cat([p.ged for p in part]))
+    assert torch.equal(full.rowmatch, torch.cat([p.rowmatch for p in part]))
+
+
+def test_sharded_equals_unsharded(cuda_device):
+    """The multi-GPU path partitions candidates and gathers objectives (sharding.py); on one GPU: solving the two
+    shards separately and scattering back gives the bits of the single-batch solve."""
+    from ppo_bihyb_b200 import sharding
+    pairs = synthetic.make_pairs("aids-30-50", 12, seed_offset=81)
+    edits = synthetic.make_edits(pairs, 16, seed_offset=81)
+    ps = PairSet.from_host(pairs, cuda_device)
+    full = _solve(ps, edits)
+    B = len(edits[0])
+    n1 = np.asarray([pairs[p][0].n for p in edits[0]])
+    n2 = np.asarray([pairs[p][1].n for p in edits[0]])
+    out = torch.empty_like(full.ged)
+    for rank in range(2):
+        idx = sharding.shard_indices(B, rank, 2, sharding.work_estimate(n1, n2))
+        local = _solve(ps, tuple(e[idx] for e in edits))
+        out[torch.as_tensor(idx, device=cuda_device)] = local.ged
+    assert torch.equal(out, full.ged)
