@@ -46,10 +46,19 @@ def parse():
     return ap.parse_args()
 
 
-def workload(args, rank):
-    from ppo_bihyb_b200 import synthetic
-    pairs = synthetic.make_pairs(args.config, args.pairs, seed_offset=100 + rank)
-    base, eu, ev = synthetic.make_edits(pairs, args.edits, seed_offset=100 + rank)
+def workload(args, rank, world=1):
+    """The job's candidate list: `pairs * world` base pairs x `edits` edge toggles, sharded over the ranks with the
+    work-balanced partition of ppo_bihyb_b200.sharding (no data-path collective: every candidate is independent).
+    Returns the base pairs and this rank's (base_idx, edit_u, edit_v)."""
+    import numpy as np
+    from ppo_bihyb_b200 import sharding, synthetic
+    pairs = synthetic.make_pairs(args.config, args.pairs * world, seed_offset=100)
+    base, eu, ev = synthetic.make_edits(pairs, args.edits, seed_offset=100)
+    if world > 1:
+        n1 = np.asarray([pairs[p][0].n for p in base])
+        n2 = np.asarray([pairs[p][1].n for p in base])
+        idx = sharding.shard_indices(len(base), rank, world, sharding.work_estimate(n1, n2))
+        base, eu, ev = base[idx], eu[idx], ev[idx]
     return pairs, base, eu, ev
 
 
@@ -179,15 +188,15 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    pairs, base, eu, ev = workload(args, rank)
+    pairs, base, eu, ev = workload(args, rank, world)
     B = len(base)
+    B_max = -(-args.pairs * args.edits * world // world)                 # shards differ by at most one candidate
     ps = PairSet.from_host(pairs, dev)
     base_d = torch.from_numpy(base).to(dev)
     eu_d, ev_d = torch.from_numpy(eu).to(dev), torch.from_numpy(ev).to(dev)
     plan = solver.make_plan(ps, base)
     host_batch = solver.HostBatch(pairs, base, eu, ev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
-    local_idx = np.arange(B, dtype=np.int64) + rank * B                  # this rank's slice of the global candidate list
 
     def barrier():
         if world > 1:
@@ -197,8 +206,10 @@ def main():
     def step_device():
         res = solver.solve_batch(ps, base_idx=base_d, edit_u=eu_d, edit_v=ev_d, max_iter=args.max_iter, plan=plan)
         if world > 1:                      # reward gather: the only collective of the path (B x 4 bytes per rank)
-            allged = torch.empty(world * B, dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(allged, res.ged)
+            mine = torch.zeros(B_max, dtype=torch.float32, device=dev)
+            mine[:B] = res.ged
+            allged = torch.empty(world * B_max, dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(allged, mine)
         return res
 
     def timed(fn, steps):
@@ -252,7 +263,7 @@ def main():
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_total, e2e_total = float(tmax[0]), float(tmax[1])
-    total_candidates = B * world
+    total_candidates = args.pairs * args.edits * world
 
     if rank == 0:
         value = total_candidates * args.steps / (ms_total * 1e-3)
@@ -290,7 +301,7 @@ def main():
                                  "fraction from ncu is in `issue_active_pct`",
                          "issue_active_pct": extra.get("issue_active_pct")},
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # reported at N=1 only
             threads = os.cpu_count() or 1
             sample = args.cpu_sample or max(128, 8 * threads)
             v, dt, idx, geds = cpu_baseline(args, sample, threads)

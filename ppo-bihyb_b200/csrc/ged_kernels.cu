@@ -371,7 +371,7 @@ struct LapSlots {
 // The expanded matrix is never formed: its real block comes from the cost store, row i's deletion entry from
 // sm.cdel[i], column a's insertion entry from sm.cins[a], everything else is +inf or 0 by construction.
 // Columns live in registers, one per (lane, slot): real column a -> lane a & 31, slot a >> 5; deletion column n2+k ->
-// lane k & 31, slot S + (k >> 5).  Tie-break key of a column:  kk << 17 | slot << 14 | lane << 9 | (row4col + 1), with
+// lane k & 31, slot S + (k >> 5).  Tie-break key of a column:  kk << 18 | slot << 14 | lane << 9 | (row4col + 1), with
 // kk = pos ^ 511 for an unassigned column (SciPy: the LAST unassigned minimum wins) and pos ^ 512 = 512 + pos for an
 // assigned one (else the FIRST minimum wins); pos = index in SciPy's `remaining` vector.  The smallest key wins.
 // `invalid` = the producer of the matrix saw NaN / -inf (scipy: RECTANGULAR_LSAP_INVALID).
@@ -405,15 +405,15 @@ __device__ int lsape_warp(const Store &store, bool invalid, int n1, int n2, cons
             const int j = (s < S) ? (lane + 32 * s) : (n2 + lane + 32 * (s - S));
             spc[s] = INFINITY;
             pth[s] = -1;
-            posk[s] = (N - 1 - j) << 17;
+            posk[s] = (N - 1 - j) << 18;
             int r4 = -1;
             if ((exist >> s) & 1u) r4 = sm.row4col[j];
-            kx[s] = (((r4 >= 0) ? 512 : 511) << 17) | (s << 14) | (lane << 9) | (r4 + 1);
+            kx[s] = (((r4 >= 0) ? 512 : 511) << 18) | (s << 14) | (lane << 9) | (r4 + 1);
             asm volatile("" : "+r"(kx[s]));          // keep it in a register (no re-derivation inside the scan loop)
         }
         unsigned live = exist;               // columns still in `remaining`
         double minVal = 0.0, rzmin = INFINITY;
-        int i = cur, lastk = N << 17;
+        int i = cur, lastk = N << 18;
         unsigned mk;
         int nsteps = 0;
         bool infeasible = false;
@@ -485,9 +485,9 @@ __device__ int lsape_warp(const Store &store, bool invalid, int n1, int n2, cons
                 if (Store::kPrefetch && real) store.row(in, cs);
             }
             // the winning column leaves `remaining`; the column at its end takes the freed position
-            lastk -= 1 << 17;
-            const int posstark = (int)((mk & 0xfffe0000u) ^ ((mk & (512u << 17)) ? (512u << 17) : (511u << 17)));
-            if (lk == mk) live &= ~(1u << ((mk >> 14) & 7u));
+            lastk -= 1 << 18;
+            const int posstark = (int)((mk & 0xfffc0000u) ^ ((mk & (512u << 18)) ? (512u << 18) : (511u << 18)));
+            if (lk == mk) live &= ~(1u << ((mk >> 14) & 15u));
 #pragma unroll
             for (int s = 0; s < 2 * S; ++s) posk[s] = (posk[s] == lastk) ? posstark : posk[s];
             if (r4star < 0) break;
@@ -495,7 +495,7 @@ __device__ int lsape_warp(const Store &store, bool invalid, int n1, int n2, cons
         }
         if (infeasible) return GED_ST_INFEASIBLE;
         steps += nsteps;
-        const int wl = (int)((mk >> 9) & 31u), ws = (int)((mk >> 14) & 7u);
+        const int wl = (int)((mk >> 9) & 31u), ws = (int)((mk >> 14) & 15u);
         const int sink = (ws < S) ? (wl + 32 * ws) : (n2 + wl + 32 * (ws - S));
 
         // dual update (scipy solve(): u[cur] += minVal; u[i] += minVal - spc[col4row[i]]; v[j] -= minVal - spc[j]);
@@ -1373,6 +1373,10 @@ int launch_solve_as(SolveParams prm, const CtaShape &c, cudaStream_t stream)
     const int wpb = c.tmem_warps + c.smem_warps;
     cudaError_t e = cudaFuncSetAttribute(ged_solve_kernel<S, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes);
     if (e != cudaSuccess) return fail_cuda(e, "ged_solve_batch");
+    if (const int carve = env_int("GED_B200_CARVEOUT", -1); carve >= 0) {       // experiments: explicit shared-memory carve-out (percent)
+        e = cudaFuncSetAttribute(ged_solve_kernel<S, TM>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        if (e != cudaSuccess) return fail_cuda(e, "ged_solve_batch");
+    }
     if (env_int("GED_B200_VERBOSE", 0))
         fprintf(stderr, "[ged_b200] solve<S=%d> count=%d max_n=(%d,%d) cta: %d tmem warps (%d cols) + %d smem warps, %d B dynamic smem\n",
                 S, prm.count, prm.pairs.max_n1, prm.pairs.max_n2, c.tmem_warps, c.tmem_cols, c.smem_warps, c.smem_bytes);

@@ -111,7 +111,7 @@ def solve_batch(pairs: PairSet, base_idx=None, edit_u=None, edit_v=None, solver:
     i32 = dict(device=dev, dtype=torch.int32)
     f32 = dict(device=dev, dtype=torch.float32)
     res = SolveResult(ged=torch.empty(B, **f32), ged_edited=torch.empty(B, **f32),
-                      rowmatch=torch.empty(B, m1, **i32), colmatch=torch.empty(B, m2, **i32),
+                      rowmatch=torch.full((B, m1), -1, **i32), colmatch=torch.full((B, m2), -1, **i32),   # -1 past n1 / n2
                       iters=torch.empty(B, **i32), status=torch.empty(B, **i32))
     # Scratch rows for the solves in flight (the iterate X and X*A2^T): one region per launch, sized by the number of
     # solves the device can hold at once, claimed row by row inside the kernel (ged_solve_desc.workspace_*).
