@@ -321,12 +321,15 @@ struct LapSlots {
         }
     }
     // exactly one slot of [LO, HI) -- slot LO + sel, sel warp-uniform -- is relaxed (the row's own deletion / insertion
-    // entry).  Up to two slots per group it is cheaper to run all of them under a lane mask; above that, branch.
+    // entry): all slots of the group run under a lane mask, or (GED_RELAX_BRANCH_MIN_S) a warp-uniform branch picks the slot.
     template <int LO, int HI, bool TRACK = true>
     static __device__ __forceinline__ void relax_one(double (&spc)[2 * S], int (&pth)[2 * S], int &improved,
                                                      const double (&v)[2 * S], double base, int i, unsigned live_lane, int sel)
     {
-        if constexpr (S <= 2) {
+#ifndef GED_RELAX_BRANCH_MIN_S
+#define GED_RELAX_BRANCH_MIN_S 9          // measured (n=80, n=100): the masked all-slots form is faster than the branch at every S
+#endif
+        if constexpr (S < GED_RELAX_BRANCH_MIN_S) {
             relax_base<LO, HI, TRACK>(spc, pth, improved, v, base, i, live_lane & ((1u << LO) << sel));
         } else if constexpr (I < 2 * S) {
             if constexpr (I >= LO && I < HI) {

@@ -1,6 +1,7 @@
 """Batched entry points over the C-ABI (``include/ged_b200.h``).  Device tensors in, device tensors out, launches on
 torch's current stream, no synchronisation unless ``check=True`` asks for the per-solve status."""
 import ctypes
+import os
 from dataclasses import dataclass, field
 from typing import Optional
 
@@ -116,12 +117,13 @@ def solve_batch(pairs: PairSet, base_idx=None, edit_u=None, edit_v=None, solver:
     # Scratch rows for the solves in flight (the iterate X and X*A2^T): one region per launch, sized by the number of
     # solves the device can hold at once, claimed row by row inside the kernel (ged_solve_desc.workspace_*).
     launches = [(0, B, m1, m2)] if (plan is None or len(plan[1]) <= 1) else list(plan[1])
-    regions, workspace, locks = [], None, None
+    regions, workspace, locks, legacy = [], None, None, False
     if solver == "ipfp" or x_init is not None:
         with torch.cuda.device(dev):
             floats = rows = 0
+            legacy = os.environ.get("GED_B200_WS_PER_CANDIDATE") == "1"      # experiments: one scratch row per candidate
             for (_, count, c1, c2) in launches:
-                slots = max(1, min(count, int(lib.ged_solve_max_resident(c1, c2))))
+                slots = B if legacy else max(1, min(count, int(lib.ged_solve_max_resident(c1, c2))))
                 stride = (c1 + 1) * (c2 + 1)
                 regions.append((floats, rows, slots, stride))
                 floats += 2 * slots * stride
@@ -152,7 +154,7 @@ def solve_batch(pairs: PairSet, base_idx=None, edit_u=None, edit_v=None, solver:
             f_off, r_off, slots, stride = regions[k]
             desc.workspace = ctypes.cast(ctypes.c_void_p(workspace.data_ptr() + 4 * f_off), _lib.c_f32p)
             desc.workspace_locks = ctypes.cast(ctypes.c_void_p(locks.data_ptr() + 4 * r_off), _lib.c_i32p)
-            desc.workspace_slots, desc.workspace_stride = slots, stride
+            desc.workspace_slots, desc.workspace_stride = (0 if legacy else slots), stride
 
     out = _lib.GedSolveOut(p(res.ged, _lib.c_f32p), p(res.ged_edited, _lib.c_f32p), p(res.rowmatch, _lib.c_i32p),
                            p(res.colmatch, _lib.c_i32p), m1, m2, p(res.iters, _lib.c_i32p), p(res.status, _lib.c_i32p),
