@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="aids-50+")
     ap.add_argument("--pairs", type=int, default=64, help="base pairs per GPU")
-    ap.add_argument("--edits", type=int, default=128, help="candidate edge edits per base pair")
+    ap.add_argument("--edits", type=int, default=256, help="candidate edge edits per base pair")
     ap.add_argument("--max-iter", type=int, default=100)
     ap.add_argument("--cpu-sample", type=int, default=0, help="candidates in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

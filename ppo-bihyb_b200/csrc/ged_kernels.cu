@@ -59,7 +59,7 @@ static int fail_cuda(cudaError_t e, const char *where)
 // the cost matrix, `cost_bytes` the n1 x n2 block a shared-memory-backed solve adds.
 // ---------------------------------------------------------------------------------------------------------------
 struct SliceLayout {
-    int off_u, off_cdel, off_cins, off_rowbuf, off_bits1, off_bits2, off_lab1, off_lab2;
+    int off_u, off_cdel, off_rowbuf, off_bits1, off_bits2, off_lab1, off_lab2;
     int off_row4col, off_col4row, off_path, off_rowmatch, off_colmatch, off_bestrow, off_bestcol;
     int bytes, cost_bytes;
 };
@@ -74,8 +74,8 @@ __host__ __device__ inline SliceLayout make_layout(int max_n1, int max_n2)
     SliceLayout L;
     int o = 0;
     L.off_u = o;        o += 8 * (Nm + 2);     // LAP row duals (fp64); K*X temporaries rs, rsP, cs alias it
-    L.off_cdel = o;     o += 4 * Rm;           // cost[i][n2]: deletion cost of row i
-    L.off_cins = o;     o += 4 * Cm;           // cost[n1][a]: insertion cost of column a
+    L.off_cdel = o;     o += 4 * (Nm + 2);     // indexed by the row r of the expanded matrix: cost[i][n2] (deletion cost of
+                                               // row i) at r = i < n1, cost[n1][a] (insertion cost of column a) at r = n1 + a
     L.off_rowbuf = o;   o += 2 * 4 * align_up(Cm, 4);   // two rows of X (double buffered) for the Y = X A2^T gathers
     L.off_bits1 = o;    o += 4 * Rm * W1;
     L.off_bits2 = o;    o += 4 * Cm * W2;
@@ -96,7 +96,7 @@ __host__ __device__ inline SliceLayout make_layout(int max_n1, int max_n2)
 struct Slice {
     double *u;
     float *rs, *rsP, *cs;                    // alias u (live only inside kv_apply / init_cost)
-    float *cdel, *cins, *rowbuf;
+    float *cdel, *rowbuf;                    // cdel[r]: deletion cost of row r < n1, insertion cost of column r - n1 above
     uint32_t *bits1, *bits2;
     int32_t *lab1, *lab2;
     int16_t *row4col, *col4row, *path, *rowmatch, *colmatch, *bestrow, *bestcol;
@@ -111,7 +111,6 @@ __device__ inline Slice carve(unsigned char *base, const SliceLayout &L, int max
     s.rsP = s.rs + (max_n1 + 1);
     s.cs = s.rsP + (max_n1 + 1);
     s.cdel = reinterpret_cast<float *>(base + L.off_cdel);
-    s.cins = reinterpret_cast<float *>(base + L.off_cins);
     s.rowbuf = reinterpret_cast<float *>(base + L.off_rowbuf);
     s.bits1 = reinterpret_cast<uint32_t *>(base + L.off_bits1);
     s.bits2 = reinterpret_cast<uint32_t *>(base + L.off_bits2);
@@ -372,7 +371,7 @@ struct LapSlots {
 // ---------------------------------------------------------------------------------------------------------------
 // LSAPE through the expanded (n1+n2)^2 LAP in SciPy's order (hungarian_lap ged_env.py:329-351; scipy rectangular_lsap).
 // The expanded matrix is never formed: its real block comes from the cost store, row i's deletion entry from
-// sm.cdel[i], column a's insertion entry from sm.cins[a], everything else is +inf or 0 by construction.
+// sm.cdel[i], column a's insertion entry from sm.cdel[n1 + a], everything else is +inf or 0 by construction.
 // Columns live in registers, one per (lane, slot): real column a -> lane a & 31, slot a >> 5; deletion column n2+k ->
 // lane k & 31, slot S + (k >> 5).  Tie-break key of a column:  kk << 18 | slot << 14 | lane << 9 | (row4col + 1), with
 // kk = pos ^ 511 for an unassigned column (SciPy: the LAST unassigned minimum wins) and pos ^ 512 = 512 + pos for an
@@ -426,7 +425,7 @@ __device__ int lsape_warp(const Store &store, bool invalid, int n1, int n2, cons
         // bookkeeping of the previous step
         bool real = i < n1;
         double ui = u[i];
-        float cx = real ? sm.cdel[i] : sm.cins[i - n1];
+        float cx = sm.cdel[i];
         float cs[S];
 #pragma unroll
         for (int s = 0; s < S; ++s) cs[s] = 0.0f;
@@ -480,17 +479,18 @@ __device__ int lsape_warp(const Store &store, bool invalid, int n1, int n2, cons
             }
 
             const int r4star = (int)(mk & 511u) - 1;
+            const unsigned lk_slot_bit = 1u << ((lk >> 14) & 15u);     // from the lane's own bid: ready before the reduction returns
             {   // operands of the next row
                 const int in = max(r4star, 0);
                 real = in < n1;
                 ui = u[in];
-                cx = real ? sm.cdel[in] : sm.cins[in - n1];
+                cx = sm.cdel[in];
                 if (Store::kPrefetch && real) store.row(in, cs);
             }
             // the winning column leaves `remaining`; the column at its end takes the freed position
             lastk -= 1 << 18;
             const int posstark = (int)((mk & 0xfffc0000u) ^ ((mk & (512u << 18)) ? (512u << 18) : (511u << 18)));
-            if (lk == mk) live &= ~(1u << ((mk >> 14) & 15u));
+            live &= ~((lk == mk) ? lk_slot_bit : 0u);
 #pragma unroll
             for (int s = 0; s < 2 * S; ++s) posk[s] = (posk[s] == lastk) ? posstark : posk[s];
             if (r4star < 0) break;
@@ -559,7 +559,7 @@ __device__ double matched_cost_sum(const Store &store, const Slice &sm, int n1, 
 #pragma unroll
     for (int s = 0; s < S; ++s) {
         const int a = lane + 32 * s;
-        if (a < n2 && sm.colmatch[a] == n1) acc = __dadd_rn(acc, (double)sm.cins[a]);
+        if (a < n2 && sm.colmatch[a] == n1) acc = __dadd_rn(acc, (double)sm.cdel[n1 + a]);
     }
     return warp_butterfly(acc);
 }
@@ -633,7 +633,7 @@ __device__ __forceinline__ void emit_cost(const Store &store, const Slice &sm, i
     if (i < n1) {
         if (t < S) store.put(i, t, c);           // tcgen05.st is warp-collective: no lane predicate around it
         if (a == n2) sm.cdel[i] = c;
-    } else if (a <= n2) sm.cins[a] = c;
+    } else if (a <= n2) sm.cdel[n1 + a] = c;
 }
 
 // heuristic_prediction_hun's node_cost_mat (ged_env.py:310-315) in closed form from node degrees.
