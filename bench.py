@@ -47,24 +47,23 @@ def parse():
 
 
 def workload(args, rank, world=1):
-    """The job's candidate list: `pairs * world` base pairs x `edits` edge toggles, sharded over the ranks with the
-    work-balanced partition of ppo_bihyb_b200.sharding (no data-path collective: every candidate is independent).
+    """The job's candidate list: `pairs` base pairs x `edits * world` edge toggles (weak scaling: the candidate fan-out
+    per base pair grows with the number of GPUs, the mix of pair sizes stays the same), sharded over the ranks with the
+    interleaved partition of ppo_bihyb_b200.sharding (no data-path collective: every candidate is independent).
     Returns the base pairs and this rank's (base_idx, edit_u, edit_v)."""
     import numpy as np
     from ppo_bihyb_b200 import sharding, synthetic
-    pairs = synthetic.make_pairs(args.config, args.pairs * world, seed_offset=100)
-    base, eu, ev = synthetic.make_edits(pairs, args.edits, seed_offset=100)
-    if world > 1:
-        n1 = np.asarray([pairs[p][0].n for p in base])
-        n2 = np.asarray([pairs[p][1].n for p in base])
-        idx = sharding.shard_indices(len(base), rank, world, sharding.work_estimate(n1, n2))
+    pairs = synthetic.make_pairs(args.config, args.pairs, seed_offset=100)
+    base, eu, ev = synthetic.make_edits(pairs, args.edits * world, seed_offset=100)
+    if world > 1:      # the list is grouped by base pair: interleaving gives every rank the same mix of pairs
+        idx = sharding.shard_indices(len(base), rank, world, interleave=True)
         base, eu, ev = base[idx], eu[idx], ev[idx]
     return pairs, base, eu, ev
 
 
 def workload_name(args, world):
     return (f"{args.config} synthetic pairs, {args.pairs} base pairs x {args.edits} edge-edit candidates per GPU "
-            f"({args.pairs * args.edits * world} candidate solves per step), max_iter {args.max_iter}")
+            f"({args.pairs * args.edits * world} candidate solves per step, interleaved over {world} GPU(s)), max_iter {args.max_iter}")
 
 
 # ---- CPU baseline: the oracle port on the box's host cores ----------------------------------------------------------

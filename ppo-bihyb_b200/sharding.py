@@ -41,9 +41,14 @@ def balanced_blocks(cost: np.ndarray, world_size: int) -> np.ndarray:
     return owner
 
 
-def shard_indices(B: int, rank: int, world_size: int, cost: Optional[np.ndarray] = None) -> np.ndarray:
+def shard_indices(B: int, rank: int, world_size: int, cost: Optional[np.ndarray] = None,
+                  interleave: bool = False) -> np.ndarray:
     """Indices (ascending) of the candidates rank ``rank`` solves.  Without a cost estimate: contiguous blocks of
-    ceil(B / world_size); with one: the LPT partition of :func:`balanced_blocks`."""
+    ceil(B / world_size); with one: the LPT partition of :func:`balanced_blocks`; ``interleave``: candidate b goes to
+    rank b % world_size -- the right choice when the list is grouped by base pair (a beam-search fan-out: the edits of one
+    pair cost almost the same, so every rank gets the same mix of pairs whatever the error of a size-based estimate)."""
+    if interleave:
+        return np.arange(rank, B, world_size, dtype=np.int64)
     if cost is None:
         per = -(-B // world_size) if B else 0
         return np.arange(min(B, rank * per), min(B, (rank + 1) * per), dtype=np.int64)

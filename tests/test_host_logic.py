@@ -94,6 +94,8 @@ def test_shard_indices_partition_and_balance():
             allidx = np.concatenate(parts) if parts else np.zeros(0, np.int64)
             assert np.array_equal(np.sort(allidx), np.arange(B))
             assert max(len(p) for p in parts) <= -(-B // world) if B else True
+        inter = [sharding.shard_indices(B, r, world, interleave=True) for r in range(world)]
+        assert np.array_equal(np.sort(np.concatenate(inter)) if B else np.zeros(0), np.arange(B))
         if B >= 1000:
             w = sharding.work_estimate(n1, n2)
             loads = [w[sharding.shard_indices(B, r, world, w)].sum() for r in range(world)]
