@@ -1113,7 +1113,9 @@ __global__ void ged_solve_kernel(SolveParams prm)
         if constexpr (TM) {
             if (warp < nt) {
                 const Slice sm = carve(smem_raw + (size_t)warp * prm.layout.bytes, prm.layout, m1, m2, false);
-                TmemCost<S> store{tmem_base + ((uint32_t)(32 * warp) << 16)};
+                uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16);
+                asm volatile("" : "+r"(taddr));      // opaque: kept in a register instead of being re-derived from %tid per row fetch
+                TmemCost<S> store{taddr};
                 solve_one<S>(prm, b, slot, sm, store);
                 done = true;
             }
