@@ -156,12 +156,17 @@ struct SmemCost {
 #pragma unroll
         for (int s = 0; s < S; ++s) cs[s] = p[32 * s];
     }
+    __device__ __forceinline__ void row_issue(int i, float (&cs)[S]) const { row(i, cs); }
+    __device__ __forceinline__ void row_wait(float (&)[S]) const {}
     __device__ __forceinline__ void flush() const { __syncwarp(); }
 };
 
 template <int S>
 struct TmemCost {
-    static constexpr bool kPrefetch = false; // tcgen05.ld + wait::ld is ~12 cycles: fetched where it is consumed
+    // Fetch a step ahead (row_issue ... row_wait) or where the row is consumed (row)?  Measured on B200: prefetching the
+    // tensor-memory row is 4-5 % SLOWER at n = 60 / 80 (tcgen05.ld + wait is ~12 cycles; the split form costs registers
+    // and a predicated issue), so the row is fetched in place.  The shared-memory store prefetches (LDS ~30 cycles).
+    static constexpr bool kPrefetch = false;
     uint32_t taddr;                          // (first lane of this warp's quarter) << 16 | first column
     __device__ __forceinline__ void put(int i, int s, float v) const
     {
@@ -189,6 +194,46 @@ struct TmemCost {
         }
 #pragma unroll
         for (int s = 0; s < S; ++s) cs[s] = __uint_as_float(r[s]);
+    }
+    // Split form for prefetching: the loads are issued here ...
+    __device__ __forceinline__ void row_issue(int i, float (&cs)[S]) const
+    {
+        const uint32_t a = taddr + (uint32_t)(i * S);
+        uint32_t r[8];
+        if constexpr (S == 1)
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(a) : "memory");
+        else if constexpr (S == 2)
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a) : "memory");
+        else if constexpr (S == 3)
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%3];\n\ttcgen05.ld.sync.aligned.32x32b.x1.b32 {%2}, [%4];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]) : "r"(a), "r"(a + 2u) : "memory");
+        else if constexpr (S == 4)
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a) : "memory");
+        else {
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[s]) : "r"(a + (uint32_t)s) : "memory");
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) cs[s] = __uint_as_float(r[s]);
+    }
+    // ... and completed here.  The destination registers are read-write operands of the wait, so that no use of them can
+    // be scheduled above it (the data of a tcgen05.ld is only defined after tcgen05.wait::ld).
+    __device__ __forceinline__ void row_wait(float (&cs)[S]) const
+    {
+        if constexpr (S == 1) asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(cs[0])::"memory");
+        else if constexpr (S == 2) asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(cs[0]), "+f"(cs[1])::"memory");
+        else if constexpr (S == 3) asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(cs[0]), "+f"(cs[1]), "+f"(cs[2])::"memory");
+        else if constexpr (S == 4)
+            asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(cs[0]), "+f"(cs[1]), "+f"(cs[2]), "+f"(cs[3])::"memory");
+        else if constexpr (S == 5)
+            asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(cs[0]), "+f"(cs[1]), "+f"(cs[2]), "+f"(cs[3]), "+f"(cs[4])::"memory");
+        else if constexpr (S == 6)
+            asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(cs[0]), "+f"(cs[1]), "+f"(cs[2]), "+f"(cs[3]), "+f"(cs[4]), "+f"(cs[5])::"memory");
+        else
+            asm volatile("tcgen05.wait::ld.sync.aligned;"
+                         : "+f"(cs[0]), "+f"(cs[1]), "+f"(cs[2]), "+f"(cs[3]), "+f"(cs[4]), "+f"(cs[5]), "+f"(cs[6])::"memory");
     }
     __device__ __forceinline__ void flush() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 };
@@ -429,7 +474,7 @@ __device__ int lsape_warp(const Store &store, bool invalid, int n1, int n2, cons
         float cs[S];
 #pragma unroll
         for (int s = 0; s < S; ++s) cs[s] = 0.0f;
-        if (Store::kPrefetch && real) store.row(i, cs);
+        if (Store::kPrefetch && real) store.row_issue(i, cs);
 
         for (;;) {
             ++nsteps;
@@ -437,7 +482,8 @@ __device__ int lsape_warp(const Store &store, bool invalid, int n1, int n2, cons
             unsigned lk = 0xffffffffu;
             bool need_min = true;
             if (real) {                      // real row: n2 substitution entries + its own deletion entry
-                if (!Store::kPrefetch) store.row(i, cs);
+                if (Store::kPrefetch) store.row_wait(cs);          // pairs with the row_issue of the previous step / prologue
+                else store.row(i, cs);
                 LapSlots<S>::relax_row(spc, pth, improved, v, cs, minVal, ui, i, live);
                 const double rd = __dsub_rn(__dadd_rn(minVal, (double)cx), ui);
                 LapSlots<S>::template relax_one<S, 2 * S, false>(spc, pth, improved, v, rd, i, (lane == (i & 31)) ? live : 0u, i >> 5);
@@ -485,7 +531,7 @@ __device__ int lsape_warp(const Store &store, bool invalid, int n1, int n2, cons
                 real = in < n1;
                 ui = u[in];
                 cx = sm.cdel[in];
-                if (Store::kPrefetch && real) store.row(in, cs);
+                if (Store::kPrefetch && real && r4star >= 0) store.row_issue(in, cs);   // never leave a fetch in flight past the search
             }
             // the winning column leaves `remaining`; the column at its end takes the freed position
             lastk -= 1 << 18;
