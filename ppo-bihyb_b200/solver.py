@@ -55,14 +55,20 @@ SIZE_CLASS_STEP = 8          # node-count granularity of the size classes (one l
 
 
 def plan_size_classes(n1: np.ndarray, n2: np.ndarray, step: int = SIZE_CLASS_STEP):
-    """Group candidates into size classes so that each launch sizes its shared-memory slice for ITS pairs, not for the
-    batch maximum (a 100-node pair needs 3x the shared memory of a 60-node pair).  Returns ``(order int32 [B],
-    classes)`` with ``classes = [(offset, count, max_n1, max_n2), ...]`` largest class first; inside a class the
-    heaviest solves come first (longest-processing-time order, so the tail of a launch is made of light solves)."""
+    """Group candidates into size classes, one launch each, so that the per-solve resources of a launch follow ITS pairs
+    and not the batch maximum.  What a solve occupies is decided by the kernel's launch shape (csrc/ged_kernels.cu,
+    plan_cta): S = ceil(max(n1, n2) / 32) register slots per lane and, with the cost matrix in tensor memory,
+    next_pow2(n1 * S) TMEM columns per CTA -- so pairs that share (S, columns) share a class.  Pairs whose matrix does not
+    fit tensor memory (> 512 columns) keep it in shared memory and are classed in `step`-node bins of max(n1, n2).
+    Returns ``(order int32 [B], classes)`` with ``classes = [(offset, count, max_n1, max_n2), ...]``, largest class first;
+    inside a class the heaviest solves come first (longest-processing-time order: the tail of a launch is light solves)."""
     n1 = np.asarray(n1, np.int64)
     n2 = np.asarray(n2, np.int64)
     m = np.maximum(n1, n2)
-    cls = (m + step - 1) // step
+    S = np.maximum((m + 31) // 32, 1)
+    cols = np.maximum(n1 * S, 32)
+    cols = 1 << np.ceil(np.log2(cols)).astype(np.int64)
+    cls = np.where(cols <= 512, S * 4096 + cols, S * 4096 + 2048 + (m + step - 1) // step)
     work = (n1 + n2) ** 3
     order = np.lexsort((-work, -cls)).astype(np.int32)
     classes, o = [], 0
