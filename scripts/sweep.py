@@ -1,0 +1,49 @@
+"""BASELINE.json configs[3]: IPFP+LAP throughput sweep on synthetic pairs, n1 = n2 = n in {20..200}, batch 4096
+(64 base pairs x 64 edge-edit candidates).  Prints a markdown table (pair-solves/s, LAP scan steps, executed-work figures).
+Usage: python scripts/sweep.py [--sizes 20,30,...] [--batch 4096]"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from ppo_bihyb_b200 import solver, synthetic
+from ppo_bihyb_b200.graphs import PairSet
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--sizes", default="20,30,40,60,80,100,150,200")
+ap.add_argument("--batch", type=int, default=4096)
+ap.add_argument("--reps", type=int, default=2)
+args = ap.parse_args()
+dev = torch.device("cuda:0")
+lib = solver._lib.require_cuda()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+print("| n | batch | ms / batch | pair-solves/s | mean IPFP iters | solves resident / SM | compulsory HBM bytes / solve | HBM GB/s (frac of 6550) |")
+print("|---|---|---|---|---|---|---|---|")
+for n in (int(x) for x in args.sizes.split(",")):
+    P = 64
+    E = max(1, args.batch // P)
+    pairs = synthetic.make_pairs(f"n={n}", P, seed_offset=7)
+    edits = synthetic.make_edits(pairs, E, seed_offset=7)
+    ps = PairSet.from_host(pairs, dev)
+    plan = solver.make_plan(ps, edits[0])
+    best = None
+    for rep in range(args.reps + 1):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = solver.solve_batch(ps, base_idx=edits[0], edit_u=edits[1], edit_v=edits[2], plan=plan)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if rep > 0:
+            best = ms if best is None else min(best, ms)
+    B = len(edits[0])
+    assert int((res.status != 0).sum()) == 0
+    with torch.cuda.device(dev):
+        resident = lib.ged_solve_max_resident(n, n) // 148
+    hbm = 2 * n * n + 16 * n + 28
+    gbs = B * hbm / (best * 1e-3) / 1e9
+    print(f"| {n} | {B} | {best:.1f} | {B / best * 1e3:,.0f} | {res.iters.float().mean().item():.1f} | {resident} | {hbm:,} | {gbs:.3f} ({gbs / 6550.1:.1e}) |", flush=True)

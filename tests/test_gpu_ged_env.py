@@ -172,3 +172,21 @@ def test_solver_dispatch_errors(cuda_device):
     bad.edge_index = bad.edge_index[:, 1:]                         # one direction missing -> asymmetric adjacency
     with pytest.raises(ValueError, match="symmetric"):
         env.solve_feasible_ged(bad, g, "ipfp")
+
+
+def test_score_kernel_on_reference_solutions(cuda_device):
+    """comp_ged of the reference's own IPFP / Hungarian solutions through ged_score_batch: exact (integer valued)."""
+    from _golden import x_to_match
+    from ppo_bihyb_b200.graphs import PairSet
+    z = load("solve_aids-30-50")
+    pairs = pairs_of(z)
+    ps = PairSet.from_host(pairs, cuda_device)
+    for key, want in (("x_ipfp", z["ged_ipfp"]), ("x_hungarian", z["ged_hungarian"])):
+        rm = torch.full((len(pairs), ps.max_n1), -1, dtype=torch.int32)
+        cm = torch.full((len(pairs), ps.max_n2), -1, dtype=torch.int32)
+        for p, x in enumerate(mats_of(z, key)):
+            r, c = x_to_match(x)
+            rm[p, :len(r)] = torch.from_numpy(r)
+            cm[p, :len(c)] = torch.from_numpy(c)
+        got = solver.score_batch(ps, rm.to(cuda_device), cm.to(cuda_device)).cpu().numpy()
+        assert np.array_equal(got, want)

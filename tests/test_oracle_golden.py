@@ -161,3 +161,16 @@ def test_closed_form_init_holds_for_arbitrary_node_costs_and_dense_graphs():
             a2 = (a2 + a2.T).astype(np.uint8)
         Cn = (rng.integers(0, 5, (n1 + 1, n2 + 1)) * 0.5).astype(np.float32)
         assert np.array_equal(go.init_cost_closed_form(a1, a2), go.init_cost_bruteforce(a1, a2, Cn)), t
+
+
+@pytest.mark.parametrize("name", ["aids-20-30", "aids-30-50", "aids-50plus"])
+def test_scoring_of_reference_solutions_is_exact(name):
+    """GEDenv.comp_ged (ged_env.py:245-253) on the reference's own solutions: x^T K x of a binary x is an integer, so the
+    factor-form score (matched node costs + one unit per ordered unpreserved edge) must equal the reference's value."""
+    z = load("solve_" + name)
+    xi, xh = mats_of(z, "x_ipfp"), mats_of(z, "x_hungarian")
+    for p, (g1, g2) in enumerate(pairs_of(z)):
+        Cn = label_node_cost(g1.labels, g2.labels)
+        for x, want in ((xi[p], z["ged_ipfp"][p]), (xh[p], z["ged_hungarian"][p])):
+            rm, cm = x_to_match(x)
+            assert go.score(g1.adj, g2.adj, Cn, rm, cm) == want
