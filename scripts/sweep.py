@@ -23,7 +23,7 @@ print("| n | batch | ms / batch | pair-solves/s | mean IPFP iters | solves resid
 print("|---|---|---|---|---|---|---|---|")
 for n in (int(x) for x in args.sizes.split(",")):
     P = 64
-    E = max(1, args.batch // P)
+    E = max(1, (args.batch if n <= 100 else args.batch // (4 if n <= 150 else 8)) // P)      # smaller batches above n=100 (stated in the table)
     pairs = synthetic.make_pairs(f"n={n}", P, seed_offset=7)
     edits = synthetic.make_edits(pairs, E, seed_offset=7)
     ps = PairSet.from_host(pairs, dev)

@@ -119,3 +119,37 @@ def test_large_graphs_five_and_seven_slots(cuda_device):
         assert float(res.ged[0]) == o["ged"] and int(res.iters[0]) == o["iters"]
         assert np.array_equal(res.rowmatch[0, :g1.n].cpu().numpy(), o["rowmatch"])
         assert np.array_equal(res.colmatch[0, :g2.n].cpu().numpy(), o["colmatch"])
+
+
+def test_edge_cases_tiny_and_degenerate_graphs(cuda_device):
+    """One- and two-node graphs, edgeless graphs, very different sizes, edits that are no-ops (u == v, out of range) or
+    that remove the only edge; an empty batch.  All against the oracle."""
+    from ppo_bihyb_b200.synthetic import HostGraph
+    rng = np.random.default_rng(5)
+
+    def graph(n, edges):
+        adj = np.zeros((n, n), np.uint8)
+        for a, b in edges:
+            adj[a, b] = adj[b, a] = 1
+        return HostGraph(adj, rng.integers(0, 3, n).astype(np.int32))
+
+    pairs = [(graph(1, []), graph(1, [])), (graph(1, []), graph(4, [(0, 1), (1, 2), (2, 3)])),
+             (graph(3, [(0, 1)]), graph(1, [])), (graph(2, [(0, 1)]), graph(2, [])),
+             (graph(5, []), graph(6, [])), (graph(2, [(0, 1)]), graph(33, [(i, i + 1) for i in range(32)])),
+             (graph(40, [(i, (i * 7 + 1) % 40) for i in range(40) if i != (i * 7 + 1) % 40]), graph(3, [(0, 1), (1, 2)]))]
+    ps = PairSet.from_host(pairs, cuda_device)
+    base = np.asarray([0, 1, 2, 3, 3, 3, 4, 5, 6, 6], np.int32)
+    eu = np.asarray([-1, 0, 0, 0, 1, 0, 2, 0, 3, 50], np.int32)
+    ev = np.asarray([-1, 0, 1, 1, 1, 7, 4, 1, 9, 2], np.int32)       # (0,0) and (1,1): u == v; 7, 50: out of range
+    res = solver.solve_batch(ps, base_idx=base, edit_u=eu, edit_v=ev, check=True)
+    for b in range(len(base)):
+        g1, g2 = pairs[base[b]]
+        u, v = int(eu[b]), int(ev[b])
+        edit = (u, v) if (u >= 0 and v >= 0 and u != v and u < g1.n and v < g1.n) else None
+        o = go.solve(g1.adj, g2.adj, label_node_cost(g1.labels, g2.labels), edit=edit)
+        assert float(res.ged[b]) == o["ged"] and float(res.ged_edited[b]) == o["ged_edited"], b
+        assert int(res.iters[b]) == o["iters"], b
+        assert np.array_equal(res.rowmatch[b, :g1.n].cpu().numpy(), o["rowmatch"]), b
+        assert np.array_equal(res.colmatch[b, :g2.n].cpu().numpy(), o["colmatch"]), b
+    empty = solver.solve_batch(ps, base_idx=np.zeros(0, np.int32), edit_u=np.zeros(0, np.int32), edit_v=np.zeros(0, np.int32))
+    assert empty.ged.shape == (0,) and empty.rowmatch.shape[0] == 0
