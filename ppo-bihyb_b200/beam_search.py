@@ -1,0 +1,102 @@
+"""Beam-search evaluation of the bi-level GED policy, batched.
+
+Reference: ``ged_ppo_bihyb_eval.py`` -- ``beam_search_step_kernel`` :11-35, ``beam_search`` :37-120, ``evaluate`` :123-166.
+The reference expands one test pair at a time and, with CUDA, calls ``ged_env.step`` for the <= beam * act_n_sel^2
+candidates of a step one after the other.  Here all live beam states of ALL pairs go through one policy forward and all
+their candidates through ONE ``GEDenv.step_batch`` launch per step; the per-pair bookkeeping (candidate order, the
+probability filter, the stable descending sort, the strict-improvement rule for the best tuple) is the reference's.
+"""
+import time
+from typing import List, Sequence
+
+import torch
+
+
+class _Beam:
+    __slots__ = ("graph_1", "reward", "acts", "probs")
+
+    def __init__(self, graph_1, reward, acts, probs):
+        self.graph_1, self.reward, self.acts, self.probs = graph_1, reward, acts, probs
+
+
+@torch.no_grad()
+def beam_search_batch(policy_model, ged_env, tuples: Sequence, max_actions: int, beam_size: int = 5) -> List[dict]:
+    """``tuples[p] = (graph_1, graph_2, ori_k, greedy_cost)``.  Returns one dict per pair with the reference's keys
+    (``reward``, ``solution``, ``acts``, ``probs``, ``time``); ``time`` is the wall time of the whole batch / #pairs."""
+    start = time.time()
+    k = beam_size                                            # act_n_sel == beam_size in the reference (:55)
+    P = len(tuples)
+    topk = [[_Beam(t[0].clone(), 0.0, [], [])] for t in tuples]
+    best = [b[0] for b in topk]
+    for _ in range(max_actions):
+        owner, g1s, g2s = [], [], []
+        for p in range(P):
+            for beam in topk[p]:
+                owner.append((p, beam))
+                g1s.append(beam.graph_1)
+                g2s.append(tuples[p][1])
+        if not owner:
+            break
+        acts1, probs1, acts2, probs2 = (t.cpu() for t in policy_model.propose(g1s, g2s, k))
+        cand = []                                            # (state index, act1, act2, prob1, prob2) in the reference's idx order
+        for s in range(len(owner)):
+            for a in range(k):
+                for b in range(k):
+                    p1, p2 = float(probs1[s, a]), float(probs2[s, a, b])
+                    if p1 > 1e-3 and p2 > 1e-3:              # :22
+                        cand.append((s, int(acts1[s, a]), int(acts2[s, a, b]), p1, p2))
+        if not cand:
+            break
+        rewards, new_graphs, _ = ged_env.step_batch(
+            [g1s[c[0]] for c in cand], [g2s[c[0]] for c in cand], [tuples[owner[c[0]][0]][2] for c in cand],
+            [torch.tensor([c[1], c[2]]) for c in cand], [tuples[owner[c[0]][0]][3] for c in cand])
+        rew = [float(r) for r in torch.cat([r.reshape(1) for r in rewards]).cpu()]
+        searched = [[] for _ in range(P)]
+        for c, r, g in zip(cand, rew, new_graphs):
+            p, beam = owner[c[0]]
+            searched[p].append(_Beam(g, r, beam.acts + [(c[1], c[2])], beam.probs + [(c[3], c[4])]))
+        for p in range(P):
+            if not searched[p]:
+                topk[p] = []
+                continue
+            searched[p].sort(key=lambda x: x.reward, reverse=True)      # stable: ties keep candidate order (:107)
+            if searched[p][0].reward > best[p].reward:                  # :108
+                best[p] = searched[p][0]
+            topk[p] = searched[p][:beam_size]                           # :112
+    dt = (time.time() - start) / max(P, 1)
+    return [{"reward": best[p].reward, "solution": float(tuples[p][3]) - best[p].reward, "acts": best[p].acts,
+             "probs": best[p].probs, "time": dt} for p in range(P)]
+
+
+def beam_search(policy_model, ged_env, inp_graph_1, inp_graph_2, ori_ks, greedy_cost, max_actions, beam_size=5,
+                multiprocess_pool=None):
+    """The reference's single-pair entry point (``ged_ppo_bihyb_eval.py:37``); ``multiprocess_pool`` is ignored."""
+    return beam_search_batch(policy_model, ged_env, [(inp_graph_1, inp_graph_2, ori_ks, greedy_cost)], max_actions, beam_size)[0]
+
+
+def evaluate(policy_net, ged_env, eval_graphs, max_steps=10, search_size=10, mp_pool=None, verbose=False):
+    """``evaluate`` (:123-166) over tuples ``(graph_1, graph_2, ori_k, ori_greedy, baselines, _)`` as ``generate_tuples``
+    returns them; all pairs are searched together.  Same result dictionary as the reference."""
+    results = beam_search_batch(policy_net, ged_env, [(t[0], t[1], t[2], t[3]) for t in eval_graphs], max_steps, search_size)
+    ret = {"reward": {}, "ratio": {}, "solution": {}, "gap": {}, "num_act": {}, "time": {}}
+    for i, (t, bs) in enumerate(zip(eval_graphs, results)):
+        ori_greedy, baselines = float(t[3]), t[4]
+        ret["reward"][f"graph{i}"] = bs["reward"]
+        ret["ratio"][f"graph{i}"] = bs["reward"] / ori_greedy
+        ret["gap"][f"graph{i}"] = (bs["solution"] - min(baselines.values())) / bs["solution"] if baselines else float("nan")
+        ret["solution"][f"graph{i}_ours"] = bs["solution"]
+        ret["num_act"][f"graph{i}"] = len(bs["acts"])
+        for key, val in (baselines or {}).items():
+            ret["solution"][f"graph{i}_{key}"] = val
+        ret["time"][f"graph{i}"] = bs["time"]
+        if verbose:
+            print(f"BEAMSEARCH \t gid {i} \t time {bs['time']:.2f} \t reward {bs['reward']:.4f} \t ratio {bs['reward'] / ori_greedy:.4f} "
+                  f"\t ours {bs['solution']:.4f} \t action {bs['acts']}")
+    for key, val in ret.items():
+        if key == "solution":
+            ours = [v for k_, v in val.items() if "ours" in k_]
+            ret[key]["mean"] = float(sum(ours) / len(ours))
+            ret[key]["std"] = float(torch.tensor(ours).std(unbiased=False))
+        else:
+            ret[key]["mean"] = sum(val.values()) / len(val)
+    return ret
