@@ -13,12 +13,13 @@ Module / parameter names equal the reference's, so its checkpoints (``pretrained
 
 Differences on purpose: padded node slots are masked out of the action soft-max (the reference never batches graphs of
 different sizes in one call -- all beam states of a pair have the pair's node count -- so per pair the probabilities are
-identical); only the inference path (greedy top-k selection, evaluation) and the value head are provided.
+identical).
 """
 from typing import List, Sequence, Tuple
 
 import torch
 from torch import nn
+from torch.distributions import Categorical
 
 
 class DenseGraphBatch:
@@ -186,8 +187,24 @@ class ActorNet(nn.Module):
             mask[rows, prev_act] = -float("inf")
         mask = mask.masked_fill(~node_mask, -float("inf"))
         act_probs = torch.softmax(act_scores + mask, dim=1)
-        acts = torch.argsort(act_probs, dim=-1, descending=True)[:, :greedy_sel_num]
-        return acts, torch.gather(act_probs, 1, acts)
+        if greedy_sel_num > 0:
+            acts = torch.argsort(act_probs, dim=-1, descending=True)[:, :greedy_sel_num]
+            return acts, torch.gather(act_probs, 1, acts)
+        return act_probs
+
+    def forward(self, state_feat, node_mask, known_action=None):
+        """``_act`` (src/ged_ppo_bihyb_model.py:84-90): sample (or score the known) first node, then the second node given
+        the first.  Returns actions [2, B], log-probabilities [2, B], entropy [B]."""
+        if known_action is None:
+            known_action = (None, None)
+        out = []
+        prev = None
+        for step in range(2):
+            dist = Categorical(probs=self.select_nodes(state_feat, node_mask, 0, prev_act=prev))
+            act = dist.sample() if known_action[step] is None else known_action[step]
+            out.append((act, dist.log_prob(act), dist.entropy()))
+            prev = act
+        return torch.stack((out[0][0], out[1][0])), torch.stack((out[0][1], out[1][1])), out[0][2] + out[1][2]
 
 
 class TensorNetworkModule(nn.Module):
@@ -226,6 +243,21 @@ class ActorCritic(nn.Module):
         self.state_encoder = GraphEncoder(node_feature_dim, node_output_size, batch_norm, one_hot_degree, gnn_layers)
         self.actor_net = ActorNet(node_output_size, batch_norm)
         self.value_net = CriticNet(node_output_size, batch_norm)
+
+    def act(self, inp_graph_1: List, inp_graph_2: List, memory):
+        """``ActorCritic.act`` (ged_ppo_bihyb_train.py:112-120): sample one edge edit per state and record it."""
+        diff_feat, _, _ = self.state_encoder(inp_graph_1, inp_graph_2)
+        actions, action_logits, _ = self.actor_net(diff_feat, self.state_encoder.last_mask)
+        memory.states.append((inp_graph_1, inp_graph_2))
+        memory.actions.append(actions)
+        memory.logprobs.append(action_logits)
+        return actions
+
+    def evaluate(self, inp_graph_1: List, inp_graph_2: List, action):
+        """``ActorCritic.evaluate`` (ged_ppo_bihyb_train.py:122-126) -> (log-probs [2, B], state value [B], entropy [B])."""
+        diff_feat, graph_feat_1, graph_feat_2 = self.state_encoder(inp_graph_1, inp_graph_2)
+        _, action_logits, entropy = self.actor_net(diff_feat, self.state_encoder.last_mask, action)
+        return action_logits, self.value_net(graph_feat_1, graph_feat_2), entropy
 
     @torch.no_grad()
     def propose(self, graphs_1: List, graphs_2: List, act_n_sel: int) -> Tuple[torch.Tensor, ...]:

@@ -1,0 +1,150 @@
+"""PPO for the bi-level GED policy with data-parallel rollouts (BASELINE.json configs[4]).
+
+Reference: ``ged_ppo_bihyb_train.py`` -- ``Memory`` :83-98, ``PPO`` :129-221 (clipped surrogate, K epochs, Adam with the
+encoder at lr/10), rollout loop :270-321.  What is different:
+
+  * the environment step of a whole batch of pairs is ONE ``GEDenv.step_batch`` launch (the reference maps
+    ``ged_env.step`` over a fork pool, :286-298);
+  * with ``torch.distributed`` initialised, every rank rolls out its own shard of the training pairs; ``update`` all-gathers
+    the discounted rewards' first two moments (so the normalisation is the global one) and all-reduces the gradients as
+    one flattened NCCL call per epoch (``sharding.allreduce_mean_``) -- the only inter-GPU traffic of a train step.
+"""
+from dataclasses import dataclass, field
+from typing import List, Sequence
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from . import sharding
+from .policy import ActorCritic
+
+
+class Memory:
+    def __init__(self):
+        self.actions, self.states, self.candidates, self.logprobs, self.rewards, self.is_terminals = [], [], [], [], [], []
+
+    def clear_memory(self):
+        for lst in (self.actions, self.states, self.candidates, self.logprobs, self.rewards, self.is_terminals):
+            del lst[:]
+
+
+@dataclass
+class PPOConfig:
+    """The keys of ``config/ppo_bihyb_ged.yaml`` that PPO reads (same names and defaults)."""
+    learning_rate: float = 0.001
+    betas: tuple = (0.9, 0.999)
+    gamma: float = 0.95
+    eps_clip: float = 0.1
+    k_epochs: int = 10
+    lr_steps: list = field(default_factory=list)
+    update_timestep: int = 10
+    node_feature_dim: int = 34
+    node_output_size: int = 64
+    batch_norm: bool = False
+    one_hot_degree: int = 0
+    gnn_layers: int = 3
+
+
+def _distributed():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+class PPO:
+    def __init__(self, args: PPOConfig, device):
+        self.lr, self.betas, self.gamma, self.eps_clip, self.K_epochs = args.learning_rate, args.betas, args.gamma, args.eps_clip, args.k_epochs
+        self.device = device
+        ac_params = args.node_feature_dim, args.node_output_size, args.batch_norm, args.one_hot_degree, args.gnn_layers
+        self.policy = ActorCritic(*ac_params).to(device)
+        self.optimizer = torch.optim.Adam(
+            [{"params": self.policy.actor_net.parameters()},
+             {"params": self.policy.value_net.parameters()},
+             {"params": self.policy.state_encoder.parameters(), "lr": self.lr / 10}],
+            lr=self.lr, betas=self.betas)
+        if len(args.lr_steps) > 0:
+            self.lr_scheduler = torch.optim.lr_scheduler.MultiStepLR(
+                self.optimizer, [s // args.update_timestep for s in args.lr_steps], gamma=0.1)
+        else:
+            self.lr_scheduler = None
+        self.policy_old = ActorCritic(*ac_params).to(device)
+        self.policy_old.load_state_dict(self.policy.state_dict())
+        self.MseLoss = nn.MSELoss()
+
+    def _discounted_rewards(self, memory):
+        with torch.no_grad():
+            _, state_values, _ = self.policy.evaluate(*memory.states[-1], memory.actions[-1].to(self.device))
+        discounted = state_values
+        rewards = []
+        for reward, is_terminal in zip(reversed(memory.rewards), reversed(memory.is_terminals)):
+            reward = torch.as_tensor([float(r) for r in reward], dtype=torch.float32, device=self.device)
+            term = torch.as_tensor([float(t) for t in is_terminal], dtype=torch.float32, device=self.device)
+            discounted = reward + self.gamma * (discounted * (1 - term))
+            rewards.insert(0, discounted)
+        return torch.cat(rewards)
+
+    def _normalise(self, rewards):
+        """(r - mean) / (std + 1e-5) with torch's unbiased std, over the rewards of ALL ranks."""
+        if not _distributed():
+            return (rewards - rewards.mean()) / (rewards.std() + 1e-5)
+        stats = torch.stack((rewards.sum(), (rewards * rewards).sum(), torch.tensor(float(rewards.numel()), device=rewards.device))).double()
+        dist.all_reduce(stats)
+        n = stats[2]
+        mean = stats[0] / n
+        var = (stats[1] - n * mean * mean) / (n - 1)
+        return ((rewards.double() - mean) / (var.clamp(min=0).sqrt() + 1e-5)).float()
+
+    def update(self, memory) -> torch.Tensor:
+        """``PPO.update`` (ged_ppo_bihyb_train.py:158-221).  Returns the mean critic loss of the K epochs."""
+        rewards = self._normalise(self._discounted_rewards(memory))
+        old_graph_1, old_graph_2 = [], []
+        for state in memory.states:
+            old_graph_1 += state[0]
+            old_graph_2 += state[1]
+        old_actions = torch.cat(memory.actions, dim=1).to(self.device)
+        old_logprobs = torch.cat(memory.logprobs, dim=1).to(self.device).detach()
+        critic_loss_sum = 0
+        params = [p for p in self.policy.parameters()]
+        for _ in range(self.K_epochs):
+            logprobs, state_values, dist_entropy = self.policy.evaluate(old_graph_1, old_graph_2, old_actions)
+            ratios = torch.exp(logprobs - old_logprobs)
+            advantages = rewards - state_values.detach()
+            surr1 = ratios * advantages
+            surr2 = torch.clamp(ratios, 1 - self.eps_clip, 1 + self.eps_clip) * advantages
+            actor_loss = -torch.min(surr1, surr2)
+            critic_loss = self.MseLoss(state_values, rewards)
+            entropy_reg = -0.01 * dist_entropy
+            critic_loss_sum = critic_loss_sum + critic_loss.detach().mean()
+            self.optimizer.zero_grad()
+            (actor_loss + critic_loss + entropy_reg).mean().backward()
+            if _distributed():          # equal shard sizes: the mean of the rank gradients is the global-batch gradient
+                sharding.allreduce_mean_([p.grad for p in params if p.grad is not None])
+            self.optimizer.step()
+        if self.lr_scheduler:
+            self.lr_scheduler.step()
+        self.policy_old.load_state_dict(self.policy.state_dict())
+        return critic_loss_sum / self.K_epochs
+
+
+def rollout_episode(ppo: PPO, env, tuples: Sequence, memory: Memory, max_timesteps: int, timestep: int, update_timestep: int):
+    """One episode of the reference's training loop (:270-321) for a batch of pairs: ``max_timesteps`` edits per pair,
+    every environment step of the batch in one ``step_batch`` launch, ``ppo.update`` whenever ``timestep`` hits the
+    update interval.  ``tuples[b] = (graph_1, graph_2, ori_k, ori_greedy, ...)``.
+    Returns (new timestep, summed reward per pair, list of critic losses)."""
+    g1 = [t[0] for t in tuples]
+    g2 = [t[1] for t in tuples]
+    ks = [t[2] for t in tuples]
+    greedy = [t[3] for t in tuples]
+    total = [0.0] * len(tuples)
+    losses = []
+    for t in range(max_timesteps):
+        timestep += 1
+        with torch.no_grad():
+            action_batch = ppo.policy_old.act(g1, g2, memory)
+        rewards, g1, greedy = env.step_batch(g1, g2, ks, action_batch.cpu(), greedy)
+        memory.rewards.append(rewards)
+        memory.is_terminals.append([t == max_timesteps - 1] * len(tuples))
+        total = [a + float(r) for a, r in zip(total, rewards)]
+        if timestep % update_timestep == 0:
+            losses.append(ppo.update(memory))
+            memory.clear_memory()
+    return timestep, total, losses
