@@ -27,7 +27,7 @@ import torch
 
 from . import _lib, solver
 from .graphs import (Data, FactoredK, PairSet, data_to_host, dense_k_from_factors, factors_from_dense_k,
-                     node_cost_matrix)
+                     host_cache_key, node_cost_matrix)
 from .synthetic import HostGraph
 
 VERY_LARGE_INT = 65536          # same sentinel as the reference (ged_env.py:14)
@@ -255,8 +255,26 @@ class GEDenv(object):
     def toggle_edge(graph_1, act):
         """The edit of ``step`` (:111-121): remove both directions of (act[0], act[1]) if either is present, else append
         both.  Returns a modified clone; the input graph is untouched."""
-        new_graph_1 = graph_1.clone()
         assert isinstance(act, torch.Tensor)
+        cached = getattr(graph_1, "_ged_host", None) if isinstance(graph_1, Data) else None
+        if cached is not None and cached[0][:3] == host_cache_key(graph_1, cached[0][5])[:3]:
+            # host view available (small graphs: decide and rebuild the edge list on the host, no device round trip)
+            new_graph_1 = graph_1.clone()
+            u, v = (int(t) for t in act.reshape(-1).tolist())
+            adj, ei = cached[1].copy(), cached[4]
+            if adj[u, v] or adj[v, u]:
+                keep = ~(((ei[0] == u) & (ei[1] == v)) | ((ei[0] == v) & (ei[1] == u)))
+                ei = ei[:, keep]
+                adj[u, v] = adj[v, u] = 0
+            else:
+                ei = np.concatenate((ei, np.asarray([[u, v], [v, u]], ei.dtype)), axis=1)
+                adj[u, v] = min(int(adj[u, v]) + 1, 255)
+                adj[v, u] = min(int(adj[v, u]) + 1, 255)
+            ei = np.ascontiguousarray(ei)
+            new_graph_1.edge_index = torch.from_numpy(ei).to(graph_1.edge_index.device, non_blocking=True)
+            new_graph_1._ged_host = (host_cache_key(new_graph_1, cached[0][5]), adj, cached[2], cached[3], ei)
+            return new_graph_1
+        new_graph_1 = graph_1.clone()
         ei = new_graph_1.edge_index
         pair = act.to(ei.device).reshape(2, 1)
         fwd = (ei == pair).all(dim=0)
@@ -266,6 +284,8 @@ class GEDenv(object):
             new_graph_1.edge_index = ei[:, ~present]
         else:
             new_graph_1.edge_index = torch.cat((ei, pair, pair.flip(0)), dim=1)
+        if isinstance(new_graph_1, Data) and hasattr(new_graph_1, "_ged_host"):
+            del new_graph_1._ged_host
         return new_graph_1
 
     def step(self, graph_1, graph_2, ori_k, act, prev_solution):
@@ -282,8 +302,8 @@ class GEDenv(object):
         if torch.is_tensor(acts):
             acts = [acts[:, b] for b in range(B)]
         dev = self._dev(*(g.x for g in graphs_1))
-        new_graphs = [self.toggle_edge(g, a) for g, a in zip(graphs_1, acts)]
-        # base pairs are deduplicated by object identity: a beam-search step evaluates act_n_sel^2 edits per beam state
+        # base pairs are deduplicated by object identity: a beam-search step evaluates act_n_sel^2 edits per beam state.
+        # The host views are built first, so that the edits below are made on the host (toggle_edge) without device round trips.
         items, index_of, base_idx, score_adjs = [], {}, [], []
         for b in range(B):
             key = (id(graphs_1[b]), id(graphs_2[b]))
@@ -294,6 +314,7 @@ class GEDenv(object):
             g1h, g2h, _ = items[index_of[key]]
             adj = self._score_graph(ori_ks[b], graphs_1[b], g1h.n, g2h.n)
             score_adjs.append(g1h.adj if adj is None else adj)
+        new_graphs = [self.toggle_edge(g, a) for g, a in zip(graphs_1, acts)]
         ps = _pairset_from_factors(items, dev)
         act_np = np.asarray([[int(a[0]), int(a[1])] for a in acts], np.int32).reshape(B, 2)
         off = np.zeros(B, np.int64)
@@ -306,7 +327,11 @@ class GEDenv(object):
                                  score_adj1=score_pool, score_adj1_off=torch.from_numpy(off).to(dev),
                                  score_idx=np.arange(B, dtype=np.int32))
         new_solutions = [res.ged[b:b + 1] for b in range(B)]
-        rewards = [prev_solutions[b] - new_solutions[b] for b in range(B)]
+        if all(not torch.is_tensor(p) for p in prev_solutions):        # one vector op instead of B tiny launches
+            rew = torch.tensor([float(p) for p in prev_solutions], dtype=torch.float32).to(dev, non_blocking=True) - res.ged
+            rewards = [rew[b:b + 1] for b in range(B)]
+        else:
+            rewards = [prev_solutions[b] - new_solutions[b] for b in range(B)]
         return rewards, new_graphs, new_solutions
 
     def solve_feasible_ged(self, graph_1, graph_2, solver_type, ori_k=None):

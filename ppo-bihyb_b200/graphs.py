@@ -57,6 +57,10 @@ def data_to_host(g, ori_feature_dim: int) -> Tuple[np.ndarray, Optional[np.ndarr
     Labels are recovered from the one-hot block ``x[:, :ori_feature_dim]`` that ``node_metric`` compares
     (reference ``ged_env.py:232-233``); if that block is not one-hot the caller must fall back to an explicit
     node-cost matrix (returned labels are None)."""
+    key = host_cache_key(g, ori_feature_dim)
+    cached = getattr(g, "_ged_host", None) if isinstance(g, Data) else None
+    if cached is not None and cached[0] == key:
+        return cached[1], cached[2], cached[3]
     x = g.x.detach().to("cpu", torch.float32).numpy()
     ei = g.edge_index.detach().to("cpu").numpy()
     n = x.shape[0]
@@ -67,7 +71,15 @@ def data_to_host(g, ori_feature_dim: int) -> Tuple[np.ndarray, Optional[np.ndarr
     labels = None
     if feat.shape[1] > 0 and np.all((feat == 0) | (feat == 1)) and np.all(feat.sum(1) == 1):
         labels = feat.argmax(1).astype(np.int32)
-    return np.minimum(adj, 255).astype(np.uint8), labels, feat
+    out = (np.minimum(adj, 255).astype(np.uint8), labels, feat)
+    if isinstance(g, Data):
+        g._ged_host = (key,) + out + (ei,)  # host view, valid while x / edge_index are the same (unmodified) tensors
+    return out
+
+
+def host_cache_key(g, ori_feature_dim: int):
+    """Identity of the tensors a host view was derived from (a new or in-place modified tensor invalidates it)."""
+    return (g.edge_index.data_ptr(), g.edge_index._version, tuple(g.edge_index.shape), g.x.data_ptr(), g.x._version, int(ori_feature_dim))
 
 
 def node_cost_matrix(feat1: np.ndarray, feat2: np.ndarray) -> np.ndarray:
@@ -137,8 +149,8 @@ class PairSet:
                           lab2=np.concatenate([g2.labels for _, g2 in pairs]).astype(np.int32) if P else np.zeros(0, np.int32),
                           lab2_off=l2_off)
         tensors = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in fields.items()}
-        if torch.cuda.is_available():
-            tensors = {k: (t.pin_memory() if t.numel() else t) for k, t in tensors.items()}
+        if torch.cuda.is_available() and sum(t.numel() * t.element_size() for t in tensors.values()) > (1 << 20):
+            tensors = {k: (t.pin_memory() if t.numel() else t) for k, t in tensors.items()}    # pinning small batches costs more than it saves
         meta = dict(max_n1=int(n1.max()) if P else 1, max_n2=int(n2.max()) if P else 1, host_n1=n1, host_n2=n2)
         return tensors, meta
 

@@ -134,9 +134,10 @@ class GraphEncoder(nn.Module):
     def device(self):
         return next(self.parameters()).device
 
-    def forward(self, input_graphs_1: List, input_graphs_2: List):
-        b1 = DenseGraphBatch.from_data_list(input_graphs_1, self.device)
-        b2 = DenseGraphBatch.from_data_list(input_graphs_2, self.device)
+    def forward(self, input_graphs_1, input_graphs_2):
+        """Lists of graphs, or two pre-built :class:`DenseGraphBatch` (PPO.update evaluates the same states K times)."""
+        b1 = input_graphs_1 if isinstance(input_graphs_1, DenseGraphBatch) else DenseGraphBatch.from_data_list(input_graphs_1, self.device)
+        b2 = input_graphs_2 if isinstance(input_graphs_2, DenseGraphBatch) else DenseGraphBatch.from_data_list(input_graphs_2, self.device)
         node_feat_1, node_feat_2 = self.siamese_gcn(b1), self.siamese_gcn(b2)
         sim_mat = torch.bmm(node_feat_1, node_feat_2.transpose(1, 2))
         sim_mat = log_sinkhorn(sim_mat, b1.num_nodes, b2.num_nodes, self.sinkhorn_iters, self.sinkhorn_tau)

@@ -17,7 +17,7 @@ import torch.distributed as dist
 from torch import nn
 
 from . import sharding
-from .policy import ActorCritic
+from .policy import ActorCritic, DenseGraphBatch
 
 
 class Memory:
@@ -100,6 +100,8 @@ class PPO:
         for state in memory.states:
             old_graph_1 += state[0]
             old_graph_2 += state[1]
+        old_graph_1 = DenseGraphBatch.from_data_list(old_graph_1, self.device)      # padded once, evaluated K times
+        old_graph_2 = DenseGraphBatch.from_data_list(old_graph_2, self.device)
         old_actions = torch.cat(memory.actions, dim=1).to(self.device)
         old_logprobs = torch.cat(memory.logprobs, dim=1).to(self.device).detach()
         critic_loss_sum = 0

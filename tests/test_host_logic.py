@@ -63,6 +63,9 @@ def test_toggle_edge_matches_reference_step_edge_lists():
         want = z["new_edge_index"][z["new_edge_index_off"][b]:z["new_edge_index_off"][b + 1]].reshape(2, -1)
         assert np.array_equal(out.edge_index.numpy(), want)
         assert torch.equal(d.edge_index, before)                    # input untouched (reference clones, :111)
+        data_to_host(d, synthetic.NUM_LABELS)                        # with a host view the edit is done on the host: same list
+        out2 = GEDenv.toggle_edge(d, torch.tensor([int(z["edit_u"][b]), int(z["edit_v"][b])]))
+        assert np.array_equal(out2.edge_index.numpy(), want) and torch.equal(d.edge_index, before)
 
 
 def test_factor_recovery_from_dense_k():
@@ -107,3 +110,21 @@ def test_gather_results_single_process():
     idx = np.asarray([5, 0, 3, 1, 4, 2])
     out = sharding.gather_results(local, idx, 6)
     assert torch.equal(out[torch.as_tensor(idx)], local)
+
+
+def test_host_view_cache_follows_edge_toggles():
+    """GEDenv.toggle_edge carries the host view (adjacency counts) over to the edited graph; it must equal what a fresh
+    conversion of the edited graph's tensors gives, through insertions, deletions and self-loop edits."""
+    g = synthetic.make_pairs("aids-20-30", 1, seed_offset=9)[0][0]
+    d = Data.from_host(g)
+    data_to_host(d, synthetic.NUM_LABELS)                          # populates the cache
+    rng = np.random.default_rng(1)
+    for step in range(40):
+        u, v = (int(t) for t in rng.integers(0, g.n, 2))
+        d = GEDenv.toggle_edge(d, torch.tensor([u, v]))
+        cached = data_to_host(d, synthetic.NUM_LABELS)
+        fresh = Data(x=d.x, edge_index=d.edge_index)               # no cache on this one
+        want = data_to_host(fresh, synthetic.NUM_LABELS)
+        assert np.array_equal(cached[0], want[0]) and np.array_equal(cached[1], want[1]), (step, u, v)
+    d.edge_index[0, 0] = (d.edge_index[0, 0] + 1) % g.n            # in-place modification invalidates the view
+    assert np.array_equal(data_to_host(d, synthetic.NUM_LABELS)[0], data_to_host(Data(x=d.x, edge_index=d.edge_index), synthetic.NUM_LABELS)[0])
