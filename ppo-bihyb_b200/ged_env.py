@@ -15,8 +15,9 @@ beam-search step or rollout step in ONE launch, results in input order (the refe
 What is different on purpose
   * ``construct_k`` returns a :class:`FactoredK` (adjacency + label factors, a few KB) instead of the dense
     ((n1+1)(n2+1))^2 fp32 matrix (55 MB at n=60).  Everything here accepts either; ``FactoredK.dense()`` expands it.
-  * dataset download / tuple caching (``process_dataset`` :25-59, ``generate_tuples`` :61-108) are out of scope: they need
-    torch_geometric, svn and network access.  Graphs are handed in by the caller.
+  * ``process_dataset`` :25-59 / ``generate_tuples`` :61-108 live in :mod:`dataset` (GEDLIB ``.gxl`` subsets, reference-format
+    cache files, no torch_geometric); the constructor only touches a dataset when ``dataset_root`` is given -- there is no
+    download (no network), graphs can always be handed in by the caller.
   * there is no CPU fallback: without a CUDA device every solver entry point raises.
 """
 import time
@@ -31,6 +32,8 @@ from .graphs import (Data, FactoredK, PairSet, data_to_host, dense_k_from_factor
 from .synthetic import HostGraph
 
 VERY_LARGE_INT = 65536          # same sentinel as the reference (ged_env.py:14)
+# datasets whose node_metric is the atom-label table (ged_env.py:231); AIDS-10-16 is the extra GEDLIB window the reader knows
+AIDS_FAMILY = ('AIDS700nef', 'AIDS-10-16', 'AIDS-20', 'AIDS-20-30', 'AIDS-30-50', 'AIDS-50-100')
 
 
 def _as_int(n) -> int:
@@ -211,15 +214,29 @@ def ipfp_ged(k, n1, n2, max_iter=100):
 # the environment (reference ged_env.py:17-253)
 # ---------------------------------------------------------------------------------------------------------------------
 class GEDenv(object):
-    available_solvers = ('hungarian', 'ipfp')     # 'rrwm' / 'beam' of the reference are baselines off this path
+    available_solvers = ('hungarian', 'ipfp', 'rrwm', 'beam')     # the reference's tuple (:22): names cache files may carry
+    native_solvers = ('hungarian', 'ipfp')                        # the ones this library runs itself
 
-    def __init__(self, solver_type='hungarian', dataset='AIDS700nef', ori_feature_dim=29, device=None, max_iter=100):
+    def __init__(self, solver_type='hungarian', dataset='AIDS700nef', ori_feature_dim=29, device=None, max_iter=100,
+                 dataset_root=None):
         self.solver_type = solver_type
         self.dataset = dataset
         self.ori_feature_dim = ori_feature_dim      # the reference derives it in process_dataset (:59)
         self.max_iter = max_iter
         self.device = torch.device(device) if device is not None else None
         assert solver_type in self.available_solvers
+        if dataset_root is not None:
+            self.process_dataset(dataset_root)
+
+    def process_dataset(self, root=None):
+        """Reference ``process_dataset`` :25-59 for the GEDLIB subsets (see :func:`dataset.process_dataset`)."""
+        from . import dataset as _dataset
+        _dataset.process_dataset(self, root)
+
+    def generate_tuples(self, graphs_dataset, num_samples, rand_id, device, cache_dir='ged_data/cache', verbose=True):
+        """Reference ``generate_tuples`` :61-108 (see :func:`dataset.generate_tuples`)."""
+        from . import dataset as _dataset
+        return _dataset.generate_tuples(self, graphs_dataset, num_samples, rand_id, device, cache_dir, verbose)
 
     # ---- helpers ---------------------------------------------------------------------------------------------------
     def _dev(self, *tensors):
@@ -228,8 +245,7 @@ class GEDenv(object):
     def _host_pair(self, graph_1, graph_2):
         a1, l1, f1 = data_to_host(graph_1, self.ori_feature_dim)
         a2, l2, f2 = data_to_host(graph_2, self.ori_feature_dim)
-        if self.dataset in ('CMU', 'Willow') or self.dataset not in ('AIDS700nef', 'AIDS-20', 'AIDS-20-30', 'AIDS-30-50',
-                                                                      'AIDS-50-100'):
+        if self.dataset not in AIDS_FAMILY:
             raise NotImplementedError(f'node_metric for dataset {self.dataset} is not on the B200 path')
         cost = None
         if l1 is None or l2 is None:
@@ -340,7 +356,7 @@ class GEDenv(object):
         return geds[0], ks[0], secs[0]
 
     def solve_feasible_ged_batch(self, graphs_1, graphs_2, solver_type, ori_ks=None):
-        if solver_type not in self.available_solvers:
+        if solver_type not in self.native_solvers:
             raise NotImplementedError(f'{solver_type} is not implemented.')       # :156
         B = len(graphs_1)
         _lib.require_cuda()
@@ -376,7 +392,7 @@ class GEDenv(object):
 
     def node_metric(self, node1, node2):
         """Reference ``node_metric`` :230-243 (batched dense features in, [B, R, C] costs out)."""
-        if self.dataset in ['AIDS700nef', 'AIDS-20', 'AIDS-20-30', 'AIDS-30-50', 'AIDS-50-100']:
+        if self.dataset in AIDS_FAMILY:
             node1, node2 = node1[:, :, :self.ori_feature_dim], node2[:, :, :self.ori_feature_dim]
             table = [0., 1., 1.]
         elif self.dataset in ['CMU', 'Willow']:

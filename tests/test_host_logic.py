@@ -79,11 +79,13 @@ def test_factor_recovery_from_dense_k():
 
 def test_unknown_solver_and_dataset_errors():
     with pytest.raises(AssertionError):
-        GEDenv(solver_type="rrwm")
+        GEDenv(solver_type="ga")                      # not in the reference's available_solvers either (ged_env.py:22-23)
     env = GEDenv("ipfp", "AIDS-20-30")
     g = Data.from_host(synthetic.make_pairs("aids-20-30", 1)[0][0])
     with pytest.raises(NotImplementedError):
         env.solve_feasible_ged(g, g, "nope")
+    with pytest.raises(NotImplementedError):
+        env.solve_feasible_ged(g, g, "beam")          # A*-beam: cache files only (dataset.generate_tuples)
     with pytest.raises(ValueError):
         GEDenv.comp_ged(torch.zeros(2), torch.zeros(2, 2))
 
