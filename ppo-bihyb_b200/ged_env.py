@@ -6,7 +6,7 @@ Reference interface mirrored here (file:line in ``/root/reference/utils/ged_env.
   ``GEDenv.step``               :110-124    ``GEDenv.solve_feasible_ged``  :140-158   ``GEDenv.construct_k`` :160-228
   ``GEDenv.node_metric``        :230-243    ``GEDenv.comp_ged``            :245-253   ``ipfp_ged``           :256-289
   ``hungarian_ged``             :303-305    ``heuristic_prediction_hun``   :308-326   ``hungarian_lap``      :329-351
-  ``hungarian``                 :354-398
+  ``hungarian``                 :354-398    ``ga_ged``                     :424-449   ``rrwm_ged``           :452-477
 
 Additions (not in the reference): ``GEDenv.step_batch`` / ``GEDenv.solve_feasible_ged_batch`` -- every candidate of a
 beam-search step or rollout step in ONE launch, results in input order (the reference loops, ``ged_ppo_bihyb_eval.py:95-100``,
@@ -26,7 +26,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 import torch
 
-from . import _lib, solver
+from . import _lib, baselines, solver
 from .graphs import (Data, FactoredK, PairSet, data_to_host, dense_k_from_factors, factors_from_dense_k,
                      host_cache_key, node_cost_matrix)
 from .synthetic import HostGraph
@@ -210,12 +210,44 @@ def ipfp_ged(k, n1, n2, max_iter=100):
     return _dense_x(res, 0, n1, n2).to(k.device)
 
 
+def _single_pairset(k, n1: int, n2: int):
+    """A one-pair PairSet for a FactoredK or a dense K of ``construct_k`` form."""
+    if isinstance(k, FactoredK):
+        assert (k.n1, k.n2) == (n1, n2)
+        if k.host_pair is not None:
+            return _pairset_from_factors([k.host_pair], k.pairset.device), k.pairset.device
+        assert k.pairset.num_pairs == 1
+        return k.pairset, k.pairset.device
+    assert len(k.shape) == 2
+    _lib.require_cuda()
+    fac = _DenseKFactors.get(k, n1, n2)
+    if fac is None:
+        raise NotImplementedError('rrwm_ged / ga_ged take a K of construct_k form (adjacency and node-cost factors)')
+    return _pairset_from_factors([fac], _default_device(k)), k.device
+
+
+def rrwm_ged(k, n1, n2, max_iter=100, sk_iter=100, alpha=0.2, beta=100):
+    """Reference ``rrwm_ged`` :452-477 -> projected 0/1 solution, (n1+1) x (n2+1)."""
+    n1, n2 = _as_int(n1), _as_int(n2)
+    ps, out_dev = _single_pairset(k, n1, n2)
+    rm, cm, _ = baselines.rrwm_batch(ps, max_iter, sk_iter, alpha, beta)
+    return solver.match_to_dense(rm[0], cm[0], n1, n2).to(out_dev)
+
+
+def ga_ged(k, n1, n2, max_iter=100, sk_iter=10, tau0=1, tau_min=0.1, gamma=0.95):
+    """Reference ``ga_ged`` :424-449 -> projected 0/1 solution, (n1+1) x (n2+1)."""
+    n1, n2 = _as_int(n1), _as_int(n2)
+    ps, out_dev = _single_pairset(k, n1, n2)
+    rm, cm = baselines.ga_batch(ps, max_iter, sk_iter, tau0, tau_min, gamma)
+    return solver.match_to_dense(rm[0], cm[0], n1, n2).to(out_dev)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # the environment (reference ged_env.py:17-253)
 # ---------------------------------------------------------------------------------------------------------------------
 class GEDenv(object):
     available_solvers = ('hungarian', 'ipfp', 'rrwm', 'beam')     # the reference's tuple (:22): names cache files may carry
-    native_solvers = ('hungarian', 'ipfp')                        # the ones this library runs itself
+    native_solvers = ('hungarian', 'ipfp', 'rrwm', 'ga')          # the ones this library runs itself ('ga': dispatch :153)
 
     def __init__(self, solver_type='hungarian', dataset='AIDS700nef', ori_feature_dim=29, device=None, max_iter=100,
                  dataset_root=None):
@@ -317,6 +349,12 @@ class GEDenv(object):
         _lib.require_cuda()
         if torch.is_tensor(acts):
             acts = [acts[:, b] for b in range(B)]
+        if self.solver_type in ('rrwm', 'ga'):      # baseline solvers: edit first, then one batched solve of the edited pairs
+            for g1, g2 in zip(graphs_1, graphs_2):
+                self._host_pair(g1, g2)             # host views, so that the edits are made on the host
+            new_graphs = [self.toggle_edge(g, a) for g, a in zip(graphs_1, acts)]
+            new_solutions, _, _ = self.solve_feasible_ged_batch(new_graphs, graphs_2, self.solver_type, list(ori_ks))
+            return [p - s for p, s in zip(prev_solutions, new_solutions)], new_graphs, new_solutions
         dev = self._dev(*(g.x for g in graphs_1))
         # base pairs are deduplicated by object identity: a beam-search step evaluates act_n_sel^2 edits per beam state.
         # The host views are built first, so that the edits below are made on the host (toggle_edge) without device round trips.
@@ -376,11 +414,22 @@ class GEDenv(object):
                       score_adj1_off=torch.from_numpy(off).to(dev), score_idx=np.arange(B, dtype=np.int32))
         torch.cuda.synchronize(dev)
         t0 = time.time()                                                          # the reference times the solve only (:142,157)
-        res = solver.solve_batch(ps, solver=solver_type, max_iter=self.max_iter, check=True, **kw)
+        if solver_type in ('rrwm', 'ga'):
+            if solver_type == 'rrwm':
+                rm, cm, _ = baselines.rrwm_batch(ps)
+            else:
+                rm, cm = baselines.ga_batch(ps)
+            score_ps = ps
+            if kw:      # comp_ged against the ORIGINAL K (:158): same graph 2 and node costs, graph 1 as ori_k encodes it
+                score_ps = _pairset_from_factors([(HostGraph(np.minimum(adjs[b], 1).astype(np.uint8), items[b][0].labels),
+                                                   items[b][1], items[b][2]) for b in range(B)], dev)
+            ged = solver.score_batch(score_ps, rm, cm)
+        else:
+            ged = solver.solve_batch(ps, solver=solver_type, max_iter=self.max_iter, check=True, **kw).ged
         torch.cuda.synchronize(dev)
         sec = (time.time() - t0) / max(B, 1)
         out_k = [ori_ks[b] if ori_ks[b] is not None else FactoredK(ps, b, items[b]) for b in range(B)]
-        return [res.ged[b:b + 1] for b in range(B)], out_k, [sec] * B
+        return [ged[b:b + 1] for b in range(B)], out_k, [sec] * B
 
     def construct_k(self, graph_1, graph_2) -> FactoredK:
         """Reference ``construct_k`` :160-228.  Returns the factor form; ``.dense()`` gives the reference's matrix
