@@ -129,7 +129,7 @@ def test_generate_tuples_needs_gpu_or_cache(root, tmp_path):
     layout.  (The GPU test in test_gpu_ged_env.py covers the compute-and-write branch.)"""
     env = ged_env.GEDenv("ipfp", "AIDS-10-16", dataset_root=root)
     pairs = dataset.sample_pairs(len(env.testing_graphs), 5, 3)
-    for solver, base in (("hungarian", 20.0), ("ipfp", 10.0), ("beam", 9.0)):
+    for solver, base in (("hungarian", 20.0), ("ipfp", 10.0), ("rrwm", 19.0), ("beam", 9.0)):
         dataset.save_cache(dataset.cache_path(str(tmp_path), solver, 5, "AIDS-10-16", 3),
                            {f"{a},{b}": (torch.tensor([base + k]), 0.5 + k) for k, (a, b) in enumerate(pairs)})
     if not torch.cuda.is_available():
@@ -138,4 +138,4 @@ def test_generate_tuples_needs_gpu_or_cache(root, tmp_path):
         return
     tuples = env.generate_tuples(env.testing_graphs, 5, 3, "cuda", cache_dir=str(tmp_path), verbose=False)
     assert [t[3] for t in tuples] == [10.0 + k for k in range(5)]
-    assert all(set(t[4]) == {"hungarian", "ipfp", "beam"} and t[5]["beam"] == 0.5 + k for k, t in enumerate(tuples))
+    assert all(set(t[4]) == {"hungarian", "ipfp", "rrwm", "beam"} and t[5]["beam"] == 0.5 + k for k, t in enumerate(tuples))

@@ -167,7 +167,7 @@ def test_solver_dispatch_errors(cuda_device):
     env = GEDenv("ipfp", "AIDS-20-30")
     g = Data.from_host(synthetic.make_pairs("aids-20-30", 1)[0][0], cuda_device)
     with pytest.raises(NotImplementedError):
-        env.solve_feasible_ged(g, g, "rrwm")
+        env.solve_feasible_ged(g, g, "beam")
     bad = g.clone()
     bad.edge_index = bad.edge_index[:, 1:]                         # one direction missing -> asymmetric adjacency
     with pytest.raises(ValueError, match="symmetric"):
@@ -213,7 +213,7 @@ def test_generate_tuples_computes_and_writes_reference_format(cuda_device, tmp_p
     for k, ((a, b), t) in enumerate(zip(pairs, tuples)):
         g1, g2, ori_k, ref_sol, sols, secs = t
         assert g1.i == env.testing_graphs[a].i and g2.i == env.testing_graphs[b].i and isinstance(ori_k, FactoredK)
-        assert set(sols) == {"hungarian", "ipfp", "beam"} and sols["beam"] == 3.0 + k and ref_sol == sols["ipfp"]
+        assert set(sols) == {"hungarian", "ipfp", "rrwm", "beam"} and sols["beam"] == 3.0 + k and ref_sol == sols["ipfp"]
         assert sols["ipfp"] <= sols["hungarian"] + 1e-6 or True            # IPFP usually improves its Hungarian start
         # the cached value is what the solver returns for the pair, and what the oracle computes
         ged, _, _ = env.solve_feasible_ged(g1, g2, "ipfp")
