@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GED_ABI_VERSION 4
+#define GED_ABI_VERSION 5
 
 /* call-level errors */
 #define GED_OK 0
@@ -92,6 +92,11 @@ typedef struct ged_solve_desc {
      * that class's max_n1/max_n2, so that shared memory per solve follows the pair's size, not the batch maximum. */
     const int32_t *order;
     int32_t order_count;
+    /* Optional work queue: one int32 on the device, ZERO when the launch starts (the caller resets it per launch).  When
+     * given, the launch is persistent: as many warps as fit the device, each pulling the next candidate of the
+     * (order-)list with an atomic increment until the list is exhausted -- a warp never idles behind a slower CTA-mate
+     * and the last wave is as short as the longest single solve.  NULL: one candidate per warp, assigned statically. */
+    int32_t *work_counter;
 } ged_solve_desc;
 
 typedef struct ged_solve_out {

@@ -38,6 +38,7 @@ namespace ged_impl {
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMaxS = 7;                       // slots per column group: graphs up to 32*7 = 224 nodes
 constexpr int kMaxSmemBytes = 227 * 1024;
+constexpr int kSmemPerSm = 228 * 1024;       // per SM, every resident CTA also reserves 1 KB
 constexpr int kMaxDeg = 6;                     // neighbour lists held in registers up to this degree (molecules: <= 5)
 constexpr int kTmemWarps = 4;                  // one warp per 32-lane quarter of tensor memory
 
@@ -910,6 +911,7 @@ struct SolveParams {
     long long ws_stride;
     const int32_t *order;
     int count;
+    int32_t *work_counter;   // device int32, zero at launch: persistent warps pull candidates from it (nullptr: static assignment)
     int tmem_warps;          // 0 or 4: warps 0..3 of every CTA keep their cost matrix in tensor memory
     int tmem_cols;           // columns allocated per CTA (power of two >= 32)
     ged_solve_out out;
@@ -1151,10 +1153,17 @@ __global__ void ged_solve_kernel(SolveParams prm)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         tmem_base = tmem_base_slot;
     }
-    const int slot = blockIdx.x * nwarps + warp;
-    if (slot < prm.count) {
+    // Work distribution: static (one candidate per warp) or, with a work counter, persistent warps pulling the next
+    // candidate of the list until it is exhausted (the list is ordered longest-first by the host layer).
+    const int gwarp = blockIdx.x * nwarps + warp;
+    const int m1 = prm.pairs.max_n1, m2 = prm.pairs.max_n2;
+    for (int slot = gwarp;;) {
+        if (prm.work_counter) {
+            if ((threadIdx.x & 31) == 0) slot = atomicAdd(prm.work_counter, 1);
+            slot = __shfl_sync(kFull, slot, 0);
+        }
+        if (slot >= prm.count) break;
         const int b = prm.order ? prm.order[slot] : slot;
-        const int m1 = prm.pairs.max_n1, m2 = prm.pairs.max_n2;
         bool done = false;
         if constexpr (TM) {
             if (warp < nt) {
@@ -1162,7 +1171,7 @@ __global__ void ged_solve_kernel(SolveParams prm)
                 uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16);
                 asm volatile("" : "+r"(taddr));      // opaque: kept in a register instead of being re-derived from %tid per row fetch
                 TmemCost<S> store{taddr};
-                solve_one<S>(prm, b, slot, sm, store);
+                solve_one<S>(prm, b, gwarp, sm, store);
                 done = true;
             }
         }
@@ -1170,8 +1179,10 @@ __global__ void ged_solve_kernel(SolveParams prm)
             unsigned char *base = smem_raw + (size_t)nt * prm.layout.bytes + (size_t)(warp - nt) * (prm.layout.bytes + prm.layout.cost_bytes);
             const Slice sm = carve(base, prm.layout, m1, m2, true);
             SmemCost<S> store{sm.cost, prm.pairs.n2[prm.base_idx ? prm.base_idx[b] : b]};
-            solve_one<S>(prm, b, slot, sm, store);
+            solve_one<S>(prm, b, gwarp, sm, store);
         }
+        if (!prm.work_counter) break;
+        __syncwarp();
     }
     if constexpr (TM) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1416,6 +1427,20 @@ static CtaShape plan_cta(const SliceLayout &L, int max_n1, int S, int regs_per_t
     return c;
 }
 
+// CTAs of this shape one SM holds at once: shared memory (1 KB reserved per CTA), tensor-memory columns, registers, warps.
+// (The occupancy API counts a tensor-memory kernel as one CTA per SM, so this is computed by hand.)
+static int resident_ctas(const CtaShape &c, int regs_per_thread)
+{
+    const int wpb = c.tmem_warps + c.smem_warps;
+    int ctas = 32;
+    ctas = min(ctas, kSmemPerSm / (c.smem_bytes + 1024));
+    if (c.tmem_cols > 0) ctas = min(ctas, 512 / c.tmem_cols);
+    ctas = min(ctas, 64 / wpb);
+    const int regs = (regs_per_thread + 7) / 8 * 8;
+    if (regs > 0) ctas = min(ctas, 65536 / (regs * 32 * wpb));
+    return ctas < 1 ? 1 : ctas;
+}
+
 template <int S, bool TM>
 int launch_solve_as(SolveParams prm, const CtaShape &c, cudaStream_t stream)
 {
@@ -1431,7 +1456,17 @@ int launch_solve_as(SolveParams prm, const CtaShape &c, cudaStream_t stream)
     if (env_int("GED_B200_VERBOSE", 0))
         fprintf(stderr, "[ged_b200] solve<S=%d> count=%d max_n=(%d,%d) cta: %d tmem warps (%d cols) + %d smem warps, %d B dynamic smem\n",
                 S, prm.count, prm.pairs.max_n1, prm.pairs.max_n2, c.tmem_warps, c.tmem_cols, c.smem_warps, c.smem_bytes);
-    ged_solve_kernel<S, TM><<<(prm.count + wpb - 1) / wpb, wpb * 32, c.smem_bytes, stream>>>(prm);
+    int grid = (prm.count + wpb - 1) / wpb;
+    if (prm.work_counter) {                                     // persistent launch: no more CTAs than the device holds at once
+        int dev = 0, sms = 0;
+        cudaFuncAttributes fa;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            cudaFuncGetAttributes(&fa, ged_solve_kernel<S, TM>) != cudaSuccess)
+            return fail(GED_E_CUDA, "ged_solve_batch: device query failed");
+        const int resident = sms * resident_ctas(c, fa.numRegs);
+        if (grid > resident) grid = resident;
+    }
+    ged_solve_kernel<S, TM><<<grid, wpb * 32, c.smem_bytes, stream>>>(prm);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(e, "ged_solve_batch");
     return GED_OK;
@@ -1466,12 +1501,7 @@ int GED_CAT(resident_solve_s, GED_TU_S)(const SliceLayout &L, int max_n1)
     cudaFuncAttributes fa;
     if (cudaFuncGetAttributes(&fa, ged_solve_kernel<GED_TU_S, true>) != cudaSuccess) return -1;
     const CtaShape c = plan_cta(L, max_n1, GED_TU_S, fa.numRegs);
-    const int wpb = c.tmem_warps + c.smem_warps;
-    int ctas = 32;
-    if (c.smem_bytes > 0) ctas = min(ctas, kMaxSmemBytes / c.smem_bytes);
-    if (c.tmem_cols > 0) ctas = min(ctas, 512 / c.tmem_cols);
-    ctas = min(ctas, 64 / wpb);
-    return (ctas < 1 ? 1 : ctas) * wpb;
+    return resident_ctas(c, fa.numRegs) * (c.tmem_warps + c.smem_warps);
 }
 int GED_CAT(launch_lsape_s, GED_TU_S)(const LsapeParams &prm, cudaStream_t stream)
 {
@@ -1558,6 +1588,7 @@ int ged_solve_batch(const ged_solve_desc *d, const ged_solve_out *o, void *strea
     if (prm.ws_stride < need) return fail(GED_E_BADARG, "ged_solve_batch: workspace_stride < (max_n1+1)*(max_n2+1)");
     prm.order = d->order;
     prm.count = d->order ? d->order_count : d->B;
+    prm.work_counter = d->work_counter;
     if (prm.count < 0 || prm.count > d->B) return fail(GED_E_BADARG, "ged_solve_batch: order_count out of range");
     if (prm.count == 0) return GED_OK;
     prm.tmem_warps = 0;

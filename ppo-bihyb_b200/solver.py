@@ -136,6 +136,8 @@ def solve_batch(pairs: PairSet, base_idx=None, edit_u=None, edit_v=None, solver:
                 rows += slots
         workspace = torch.empty(floats, **f32)
         locks = torch.zeros(rows, **i32)
+    # one work counter per launch: persistent warps pull candidates from it (ged_solve_desc.work_counter)
+    counters = torch.zeros(len(launches), **i32) if os.environ.get("GED_B200_WORK_QUEUE", "1") != "0" else None
     if x_init is not None:
         x_init = x_init.to(**f32).contiguous()
         assert x_init.numel() == B * ms, "x_init must be [B, mat_stride]"
@@ -153,9 +155,11 @@ def solve_batch(pairs: PairSet, base_idx=None, edit_u=None, edit_v=None, solver:
     desc = _lib.GedSolveDesc(pairs.c_struct(), B, p(base_idx, _lib.c_i32p), p(edit_u, _lib.c_i32p), p(edit_v, _lib.c_i32p),
                              p(score_adj1, _lib.c_u8p), p(score_adj1_off, _lib.c_i64p), p(score_idx, _lib.c_i32p),
                              int(max_iter), SOLVERS[solver], p(x_init, _lib.c_f32p), ms, p(workspace, _lib.c_f32p),
-                             p(locks, _lib.c_i32p), 0, 0, p(None, _lib.c_i32p), 0)
+                             p(locks, _lib.c_i32p), 0, 0, p(None, _lib.c_i32p), 0, p(None, _lib.c_i32p))
 
     def set_region(k):
+        if counters is not None:
+            desc.work_counter = ctypes.cast(ctypes.c_void_p(counters.data_ptr() + 4 * k), _lib.c_i32p)
         if regions:
             f_off, r_off, slots, stride = regions[k]
             desc.workspace = ctypes.cast(ctypes.c_void_p(workspace.data_ptr() + 4 * f_off), _lib.c_f32p)
@@ -194,6 +198,8 @@ def solve_batch(pairs: PairSet, base_idx=None, edit_u=None, edit_v=None, solver:
     if workspace is not None:
         workspace.record_stream(torch.cuda.current_stream(dev))
         locks.record_stream(torch.cuda.current_stream(dev))
+    if counters is not None:
+        counters.record_stream(torch.cuda.current_stream(dev))
     if check:
         res.raise_on_error()
     return res
