@@ -158,7 +158,7 @@ struct SmemCost {
         for (int s = 0; s < S; ++s) cs[s] = p[32 * s];
     }
     __device__ __forceinline__ void row_issue(int i, float (&cs)[S]) const { row(i, cs); }
-    __device__ __forceinline__ void row_wait(float (&)[S]) const {}
+    __device__ __forceinline__ void row_wait(int, float (&)[S]) const {}
     __device__ __forceinline__ void flush() const { __syncwarp(); }
 };
 
@@ -221,7 +221,7 @@ struct TmemCost {
     }
     // ... and completed here.  The destination registers are read-write operands of the wait, so that no use of them can
     // be scheduled above it (the data of a tcgen05.ld is only defined after tcgen05.wait::ld).
-    __device__ __forceinline__ void row_wait(float (&cs)[S]) const
+    __device__ __forceinline__ void row_wait(int, float (&cs)[S]) const
     {
         if constexpr (S == 1) asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(cs[0])::"memory");
         else if constexpr (S == 2) asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(cs[0]), "+f"(cs[1])::"memory");
@@ -237,6 +237,43 @@ struct TmemCost {
                          : "+f"(cs[0]), "+f"(cs[1]), "+f"(cs[2]), "+f"(cs[3]), "+f"(cs[4]), "+f"(cs[5]), "+f"(cs[6])::"memory");
     }
     __device__ __forceinline__ void flush() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+};
+
+// Hybrid CTAs (tensor-memory warps + shared-memory warps side by side) run ONE instantiation of the solve for both kinds
+// of warp: the store is chosen by a warp-uniform flag at each access.  Two instantiations would double the hot code
+// (IPFP iteration body ~59 KB each) and the two kinds of warp then evict each other's loops from the 32 KB instruction
+// cache (ncu: stall_no_instruction 0.12 -> 1.04 per issue, no gain from the extra warps).  Prefetch policy per kind is
+// kept: the shared-memory row is issued a step ahead (row_issue), the tensor-memory row is fetched where it is
+// consumed (row_wait carries the row index for that).
+template <int S>
+struct AnyCost {
+    static constexpr bool kPrefetch = true;
+    TmemCost<S> t;
+    SmemCost<S> m;
+    bool tm;                                 // warp-uniform
+    __device__ __forceinline__ void put(int i, int s, float v) const
+    {
+        if (tm) t.put(i, s, v);
+        else m.put(i, s, v);
+    }
+    __device__ __forceinline__ void row(int i, float (&cs)[S]) const
+    {
+        if (tm) t.row(i, cs);
+        else m.row(i, cs);
+    }
+    __device__ __forceinline__ void row_issue(int i, float (&cs)[S]) const
+    {
+        if (!tm) m.row(i, cs);
+    }
+    __device__ __forceinline__ void row_wait(int i, float (&cs)[S]) const
+    {
+        if (tm) t.row(i, cs);
+    }
+    __device__ __forceinline__ void flush() const
+    {
+        if (tm) t.flush();
+        else m.flush();
+    }
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -483,7 +520,7 @@ __device__ int lsape_warp(const Store &store, bool invalid, int n1, int n2, cons
             unsigned lk = 0xffffffffu;
             bool need_min = true;
             if (real) {                      // real row: n2 substitution entries + its own deletion entry
-                if (Store::kPrefetch) store.row_wait(cs);          // pairs with the row_issue of the previous step / prologue
+                if (Store::kPrefetch) store.row_wait(i, cs);       // pairs with the row_issue of the previous step / prologue
                 else store.row(i, cs);
                 LapSlots<S>::relax_row(spc, pth, improved, v, cs, minVal, ui, i, live);
                 const double rd = __dsub_rn(__dadd_rn(minVal, (double)cx), ui);
@@ -1134,9 +1171,15 @@ __device__ void solve_one(const SolveParams &prm, int b, int slot, const Slice &
 // tmem_warps slices without a cost block, then the others with one.
 // TM = false: no tensor-memory instruction in the binary at all (a CTA of a kernel that may allocate tensor memory holds
 // the SM's allocation permit until it relinquishes it, which keeps other CTAs off the SM).
-template <int S, bool TM>
-__global__ void ged_solve_kernel(SolveParams prm)
+constexpr int kMaxCtaWarps = 8;          // 4 tensor-memory warps + at most 4 shared-memory warps
+constexpr int kModeSmem = 0, kModeTmem = 1, kModeHybrid = 2;   // cost store of the CTA's warps: all shared / all tensor memory / both
+
+// S <= 3 (pairs up to 96 nodes): two 8-warp CTAs, or four 4-warp CTAs, must fit the register file -> at most 128 registers
+// per thread (registers are allocated per CTA in units of 4 warps: a 7-warp CTA at 136 registers is alone on its SM).
+template <int S, int MODE>
+__global__ void __launch_bounds__(32 * kMaxCtaWarps, S <= 3 ? 2 : 1) ged_solve_kernel(SolveParams prm)
 {
+    constexpr bool TM = MODE != kModeSmem;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t tmem_base_slot;
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -1157,6 +1200,12 @@ __global__ void ged_solve_kernel(SolveParams prm)
     // candidate of the list until it is exhausted (the list is ordered longest-first by the host layer).
     const int gwarp = blockIdx.x * nwarps + warp;
     const int m1 = prm.pairs.max_n1, m2 = prm.pairs.max_n2;
+    const bool tm = TM && warp < nt;         // this warp keeps its cost matrix in tensor memory (lane quarter = warp id)
+    const Slice sm = tm ? carve(smem_raw + (size_t)warp * prm.layout.bytes, prm.layout, m1, m2, false)
+                        : carve(smem_raw + (size_t)nt * prm.layout.bytes + (size_t)(warp - nt) * (prm.layout.bytes + prm.layout.cost_bytes),
+                                prm.layout, m1, m2, true);
+    uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16);
+    asm volatile("" : "+r"(taddr));          // opaque: kept in a register instead of being re-derived from %tid per row fetch
     for (int slot = gwarp;;) {
         if (prm.work_counter) {
             if ((threadIdx.x & 31) == 0) slot = atomicAdd(prm.work_counter, 1);
@@ -1164,21 +1213,15 @@ __global__ void ged_solve_kernel(SolveParams prm)
         }
         if (slot >= prm.count) break;
         const int b = prm.order ? prm.order[slot] : slot;
-        bool done = false;
-        if constexpr (TM) {
-            if (warp < nt) {
-                const Slice sm = carve(smem_raw + (size_t)warp * prm.layout.bytes, prm.layout, m1, m2, false);
-                uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16);
-                asm volatile("" : "+r"(taddr));      // opaque: kept in a register instead of being re-derived from %tid per row fetch
-                TmemCost<S> store{taddr};
-                solve_one<S>(prm, b, gwarp, sm, store);
-                done = true;
-            }
-        }
-        if (!done) {
-            unsigned char *base = smem_raw + (size_t)nt * prm.layout.bytes + (size_t)(warp - nt) * (prm.layout.bytes + prm.layout.cost_bytes);
-            const Slice sm = carve(base, prm.layout, m1, m2, true);
-            SmemCost<S> store{sm.cost, prm.pairs.n2[prm.base_idx ? prm.base_idx[b] : b]};
+        const int n2 = prm.pairs.n2[prm.base_idx ? prm.base_idx[b] : b];
+        if constexpr (MODE == kModeTmem) {
+            TmemCost<S> store{taddr};
+            solve_one<S>(prm, b, gwarp, sm, store);
+        } else if constexpr (MODE == kModeHybrid) {
+            AnyCost<S> store{TmemCost<S>{taddr}, SmemCost<S>{sm.cost, n2}, tm};
+            solve_one<S>(prm, b, gwarp, sm, store);
+        } else {
+            SmemCost<S> store{sm.cost, n2};
             solve_one<S>(prm, b, gwarp, sm, store);
         }
         if (!prm.work_counter) break;
@@ -1408,8 +1451,9 @@ static CtaShape plan_cta(const SliceLayout &L, int max_n1, int S, int regs_per_t
         if (budget < kTmemWarps * L.bytes) k = -1;
         // measured on B200 (profiles/): the solve is close to issue-bound once ~8-16 warps per SM are in flight, so extra
         // shared-memory-backed warps only pay when tensor memory can serve a single CTA per SM (n1 * S > 256 columns)
-        if ((mode == 1 || q >= 2) && k > 0) k = 0;
-        const int kmax = max_warps_by_regs / q - kTmemWarps;
+        if ((mode == 1 || q >= 4) && k > 0) k = 0;
+        int kmax = max_warps_by_regs / q / 4 * 4 - kTmemWarps;           // registers are allocated in units of 4 warps per CTA
+        if (kmax > kMaxCtaWarps - kTmemWarps) kmax = kMaxCtaWarps - kTmemWarps;  // __launch_bounds__ of the solve kernel
         if (k > kmax) k = kmax;
         const int kforce = env_int("GED_B200_SMEM_WARPS", -1);
         if (kforce >= 0) { k = (budget - kTmemWarps * L.bytes) / big; if (k > kmax) k = kmax; if (kforce < k) k = kforce; }
@@ -1437,20 +1481,20 @@ static int resident_ctas(const CtaShape &c, int regs_per_thread)
     if (c.tmem_cols > 0) ctas = min(ctas, 512 / c.tmem_cols);
     ctas = min(ctas, 64 / wpb);
     const int regs = (regs_per_thread + 7) / 8 * 8;
-    if (regs > 0) ctas = min(ctas, 65536 / (regs * 32 * wpb));
+    if (regs > 0) ctas = min(ctas, 65536 / (regs * 32 * ((wpb + 3) / 4 * 4)));     // allocated in units of 4 warps
     return ctas < 1 ? 1 : ctas;
 }
 
-template <int S, bool TM>
+template <int S, int MODE>
 int launch_solve_as(SolveParams prm, const CtaShape &c, cudaStream_t stream)
 {
     prm.tmem_warps = c.tmem_warps;
     prm.tmem_cols = c.tmem_cols;
     const int wpb = c.tmem_warps + c.smem_warps;
-    cudaError_t e = cudaFuncSetAttribute(ged_solve_kernel<S, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(ged_solve_kernel<S, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes);
     if (e != cudaSuccess) return fail_cuda(e, "ged_solve_batch");
     if (const int carve = env_int("GED_B200_CARVEOUT", -1); carve >= 0) {       // experiments: explicit shared-memory carve-out (percent)
-        e = cudaFuncSetAttribute(ged_solve_kernel<S, TM>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        e = cudaFuncSetAttribute(ged_solve_kernel<S, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (e != cudaSuccess) return fail_cuda(e, "ged_solve_batch");
     }
     if (env_int("GED_B200_VERBOSE", 0))
@@ -1461,26 +1505,37 @@ int launch_solve_as(SolveParams prm, const CtaShape &c, cudaStream_t stream)
         int dev = 0, sms = 0;
         cudaFuncAttributes fa;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-            cudaFuncGetAttributes(&fa, ged_solve_kernel<S, TM>) != cudaSuccess)
+            cudaFuncGetAttributes(&fa, ged_solve_kernel<S, MODE>) != cudaSuccess)
             return fail(GED_E_CUDA, "ged_solve_batch: device query failed");
         const int resident = sms * resident_ctas(c, fa.numRegs);
         if (grid > resident) grid = resident;
     }
-    ged_solve_kernel<S, TM><<<grid, wpb * 32, c.smem_bytes, stream>>>(prm);
+    ged_solve_kernel<S, MODE><<<grid, wpb * 32, c.smem_bytes, stream>>>(prm);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(e, "ged_solve_batch");
     return GED_OK;
+}
+
+// registers per thread the CTA shape is planned with: the larger of the tensor-memory and the hybrid instantiation
+template <int S>
+int solve_regs()
+{
+    cudaFuncAttributes a, b;
+    if (cudaFuncGetAttributes(&a, ged_solve_kernel<S, kModeTmem>) != cudaSuccess) return -1;
+    if (cudaFuncGetAttributes(&b, ged_solve_kernel<S, kModeHybrid>) != cudaSuccess) return -1;
+    return a.numRegs > b.numRegs ? a.numRegs : b.numRegs;
 }
 
 template <int S>
 int launch_solve(const SolveParams &prm, cudaStream_t stream)
 {
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, ged_solve_kernel<S, true>);
-    if (e != cudaSuccess) return fail_cuda(e, "ged_solve_batch");
-    const CtaShape c = plan_cta(prm.layout, prm.pairs.max_n1, S, fa.numRegs);
+    const int regs = solve_regs<S>();
+    if (regs < 0) return fail(GED_E_CUDA, "ged_solve_batch: cudaFuncGetAttributes failed");
+    const CtaShape c = plan_cta(prm.layout, prm.pairs.max_n1, S, regs);
     if (c.smem_bytes > kMaxSmemBytes) return fail(GED_E_TOO_LARGE, "pair too large for one warp's shared-memory slice");
-    return c.tmem_warps > 0 ? launch_solve_as<S, true>(prm, c, stream) : launch_solve_as<S, false>(prm, c, stream);
+    if (c.tmem_warps > 0 && c.smem_warps > 0) return launch_solve_as<S, kModeHybrid>(prm, c, stream);
+    return c.tmem_warps > 0 ? launch_solve_as<S, kModeTmem>(prm, c, stream) : launch_solve_as<S, kModeSmem>(prm, c, stream);
 }
 
 // ---- per-S entry points (one translation unit each) and their dispatch ---------------------------------------------------
@@ -1498,10 +1553,10 @@ int GED_CAT(launch_solve_s, GED_TU_S)(const SolveParams &prm, cudaStream_t strea
 // solves of one launch that fit one SM at once (CTAs per SM by tensor-memory columns / shared memory / registers x warps per CTA)
 int GED_CAT(resident_solve_s, GED_TU_S)(const SliceLayout &L, int max_n1)
 {
-    cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, ged_solve_kernel<GED_TU_S, true>) != cudaSuccess) return -1;
-    const CtaShape c = plan_cta(L, max_n1, GED_TU_S, fa.numRegs);
-    return resident_ctas(c, fa.numRegs) * (c.tmem_warps + c.smem_warps);
+    const int regs = solve_regs<GED_TU_S>();
+    if (regs < 0) return -1;
+    const CtaShape c = plan_cta(L, max_n1, GED_TU_S, regs);
+    return resident_ctas(c, regs) * (c.tmem_warps + c.smem_warps);
 }
 int GED_CAT(launch_lsape_s, GED_TU_S)(const LsapeParams &prm, cudaStream_t stream)
 {

@@ -7,13 +7,13 @@ from ppo_bihyb_b200.graphs import PairSet
 
 dev = torch.device("cuda:0")
 ks = [int(a) for a in sys.argv[1].split(",")] if len(sys.argv) > 1 else [-1]
-for config, P, E in (("aids-50+", 64, 256), ("n=60", 64, 128), ("n=70", 64, 64), ("n=80", 64, 64), ("n=100", 32, 64), ("aids-30-50", 64, 128)):
+for config, P, E in (("aids-50+", 64, 256), ("n=60", 64, 128), ("n=70", 64, 64), ("n=80", 64, 64), ("n=100", 32, 64), ("n=120", 32, 32)):
     pairs = synthetic.make_pairs(config, P)
     edits = synthetic.make_edits(pairs, E)
     ps = PairSet.from_host(pairs, dev)
     ref = None
-    for q in (0, 1):
-        for k in (ks if q else [-1]):
+    for q in (1,):
+        for k in ks:
             os.environ["GED_B200_WORK_QUEUE"] = str(q)
             os.environ["GED_B200_SMEM_WARPS"] = str(k)
             best = 1e9
