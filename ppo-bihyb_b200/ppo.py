@@ -7,7 +7,8 @@ encoder at lr/10), rollout loop :270-321.  What is different:
     ``ged_env.step`` over a fork pool, :286-298);
   * with ``torch.distributed`` initialised, every rank rolls out its own shard of the training pairs; ``update`` all-gathers
     the discounted rewards' first two moments (so the normalisation is the global one) and all-reduces the gradients as
-    one flattened NCCL call per epoch (``sharding.allreduce_mean_``) -- the only inter-GPU traffic of a train step.
+    one NCCL call per epoch on a flat gradient bucket the parameters' ``.grad`` are views of -- the only inter-GPU traffic
+    of a train step.
 """
 from dataclasses import dataclass, field
 from typing import List, Sequence
@@ -16,7 +17,6 @@ import torch
 import torch.distributed as dist
 from torch import nn
 
-from . import sharding
 from .policy import ActorCritic, DenseGraphBatch
 
 
@@ -69,6 +69,14 @@ class PPO:
         self.policy_old = ActorCritic(*ac_params).to(device)
         self.policy_old.load_state_dict(self.policy.state_dict())
         self.MseLoss = nn.MSELoss()
+        # One flat gradient bucket, every p.grad a view into it: zeroing is one fill, the data-parallel reduction is one
+        # NCCL call on the bucket itself (no gather / scatter copies of the 77 parameter gradients per epoch).
+        params = list(self.policy.parameters())
+        self._flat_grad = torch.zeros(sum(p.numel() for p in params), device=device)
+        o = 0
+        for p in params:
+            p.grad = self._flat_grad[o:o + p.numel()].view_as(p)
+            o += p.numel()
 
     def _discounted_rewards(self, memory):
         with torch.no_grad():
@@ -105,7 +113,6 @@ class PPO:
         old_actions = torch.cat(memory.actions, dim=1).to(self.device)
         old_logprobs = torch.cat(memory.logprobs, dim=1).to(self.device).detach()
         critic_loss_sum = 0
-        params = [p for p in self.policy.parameters()]
         for _ in range(self.K_epochs):
             logprobs, state_values, dist_entropy = self.policy.evaluate(old_graph_1, old_graph_2, old_actions)
             ratios = torch.exp(logprobs - old_logprobs)
@@ -116,10 +123,11 @@ class PPO:
             critic_loss = self.MseLoss(state_values, rewards)
             entropy_reg = -0.01 * dist_entropy
             critic_loss_sum = critic_loss_sum + critic_loss.detach().mean()
-            self.optimizer.zero_grad()
-            (actor_loss + critic_loss + entropy_reg).mean().backward()
+            self._flat_grad.zero_()
+            (actor_loss + critic_loss + entropy_reg).mean().backward()      # accumulates in place into the bucket views
             if _distributed():          # equal shard sizes: the mean of the rank gradients is the global-batch gradient
-                sharding.allreduce_mean_([p.grad for p in params if p.grad is not None])
+                dist.all_reduce(self._flat_grad)
+                self._flat_grad /= dist.get_world_size()
             self.optimizer.step()
         if self.lr_scheduler:
             self.lr_scheduler.step()
