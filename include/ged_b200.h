@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GED_ABI_VERSION 5
+#define GED_ABI_VERSION 6
 
 /* call-level errors */
 #define GED_OK 0
@@ -54,6 +54,10 @@ typedef struct ged_pairs {
     const int32_t *lab2; const int64_t *lab2_off;
     const float *node_cost; const int64_t *node_cost_off;  /* optional */
     int32_t max_n1, max_n2;                   /* host-known upper bounds over the set (sizes shared memory) */
+    /* Row stride (bytes) of every adjacency matrix of graph 1 / graph 2; 0 = compact (stride n1 / n2).  A non-zero stride
+     * lets the solver read graphs where another consumer keeps them, e.g. a padded [P, N, N] uint8 batch that the
+     * policy network also reads and that edits are applied to in place on the device (adj1_off[p] = p * N * N). */
+    int32_t adj1_ld, adj2_ld;
 } ged_pairs;
 
 /* One batch of B candidate solves.  Candidate b works on base pair base_idx[b] (identity if NULL, then
@@ -70,6 +74,7 @@ typedef struct ged_solve_desc {
      * scored with graph 1 := the n1 x n1 uint8 adjacency at score_adj1 + score_adj1_off[score_idx[b]] (same n1,
      * same labels, same graph 2); otherwise with the base pair's own unedited graph 1. */
     const uint8_t *score_adj1; const int64_t *score_adj1_off; const int32_t *score_idx;
+    int32_t score_adj1_ld;   /* row stride of the scoring adjacencies, 0 = compact (n1) */
     int32_t max_iter;        /* ipfp_ged's max_iter (100 in the reference) */
     int32_t solver_kind;     /* GED_SOLVER_* */
     /* Optional teacher forcing: start IPFP from x_init instead of the Hungarian initialiser.  Candidate b's R x C

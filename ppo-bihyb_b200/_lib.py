@@ -19,7 +19,7 @@ c_u64p = ctypes.POINTER(ctypes.c_ulonglong)
 GED_OK, GED_E_BADARG, GED_E_TOO_LARGE, GED_E_CUDA = 0, 1, 2, 3
 GED_ST_INVALID_COST, GED_ST_INFEASIBLE, GED_ST_BAD_GRAPH = 1, 2, 4
 GED_SOLVER_IPFP, GED_SOLVER_HUNGARIAN = 0, 1
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # every symbol include/ged_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED_SYMBOLS = (
@@ -39,6 +39,7 @@ class GedPairs(ctypes.Structure):
         ("lab2", c_i32p), ("lab2_off", c_i64p),
         ("node_cost", c_f32p), ("node_cost_off", c_i64p),
         ("max_n1", ctypes.c_int32), ("max_n2", ctypes.c_int32),
+        ("adj1_ld", ctypes.c_int32), ("adj2_ld", ctypes.c_int32),
     ]
 
 
@@ -49,6 +50,7 @@ class GedSolveDesc(ctypes.Structure):
         ("base_idx", c_i32p),
         ("edit_u", c_i32p), ("edit_v", c_i32p),
         ("score_adj1", c_u8p), ("score_adj1_off", c_i64p), ("score_idx", c_i32p),
+        ("score_adj1_ld", ctypes.c_int32),
         ("max_iter", ctypes.c_int32),
         ("solver_kind", ctypes.c_int32),
         ("x_init", c_f32p),

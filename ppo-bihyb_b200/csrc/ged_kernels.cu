@@ -302,14 +302,15 @@ __device__ __forceinline__ float node_cost_at(const Pair &P, const Slice &s, int
 
 // Pack one graph's uint8 adjacency into bit rows (diagonal removed, ged_env.py:209).  rows = n + 1 (dummy row zero).
 // Returns a warp-uniform flag: true if some off-diagonal entry is > 1 or the matrix is not symmetric.
-__device__ inline bool load_bits(const uint8_t *adj, int n, int W, uint32_t *bits, int lane)
+__device__ inline bool load_bits(const uint8_t *adj, int n, int ld, int W, uint32_t *bits, int lane)
 {
     bool bad = false;
+    if (ld <= 0) ld = n;                     // compact
     for (int i = 0; i < n; ++i)
         for (int w = 0; w < W; ++w) {
             const int j = w * 32 + lane;
             unsigned val = 0, tval = 0;
-            if (j < n && j != i) { val = adj[(int64_t)i * n + j]; tval = adj[(int64_t)j * n + i]; }
+            if (j < n && j != i) { val = adj[(int64_t)i * ld + j]; tval = adj[(int64_t)j * ld + i]; }
             bad |= (val > 1u) || ((val != 0) != (tval != 0));
             const unsigned word = __ballot_sync(kFull, val != 0);
             if (lane == 0) bits[i * W + w] = word;
@@ -937,6 +938,7 @@ struct SolveParams {
     int B;
     const int32_t *base_idx, *edit_u, *edit_v;
     const uint8_t *score_adj1;
+    int score_ld;
     const int64_t *score_adj1_off;
     const int32_t *score_idx;
     int max_iter, solver_kind;
@@ -966,8 +968,8 @@ __device__ inline void load_pair(const ged_pairs &pp, int p, const Slice &sm, Pa
     P.W1 = (P.n1 + 31) / 32 > 0 ? (P.n1 + 31) / 32 : 1;
     P.W2 = (P.n2 + 31) / 32 > 0 ? (P.n2 + 31) / 32 : 1;
     P.node_cost = pp.node_cost ? pp.node_cost + pp.node_cost_off[p] : nullptr;
-    const bool bad1 = load_bits(pp.adj1 + pp.adj1_off[p], P.n1, P.W1, sm.bits1, lane);
-    const bool bad2 = load_bits(pp.adj2 + pp.adj2_off[p], P.n2, P.W2, sm.bits2, lane);
+    const bool bad1 = load_bits(pp.adj1 + pp.adj1_off[p], P.n1, pp.adj1_ld, P.W1, sm.bits1, lane);
+    const bool bad2 = load_bits(pp.adj2 + pp.adj2_off[p], P.n2, pp.adj2_ld, P.W2, sm.bits2, lane);
     if (bad1 || bad2) status |= GED_ST_BAD_GRAPH;
     if (!P.node_cost) {
         const int32_t *l1 = pp.lab1 + pp.lab1_off[p], *l2 = pp.lab2 + pp.lab2_off[p];
@@ -1122,7 +1124,7 @@ __device__ void solve_one(const SolveParams &prm, int b, int slot, const Slice &
         ged_base = ged_edit;
         if (prm.score_adj1) {               // score on the original pair's graph 1 (ori_k)
             __syncwarp();
-            const bool bad = load_bits(prm.score_adj1 + prm.score_adj1_off[prm.score_idx[b]], n1, P.W1, sm.bits1, lane);
+            const bool bad = load_bits(prm.score_adj1 + prm.score_adj1_off[prm.score_idx[b]], n1, prm.score_ld, P.W1, sm.bits1, lane);
             __syncwarp();
             if (bad) status |= GED_ST_BAD_GRAPH;
             const int nnz1o = count_bits(sm.bits1, P.R * P.W1);
@@ -1629,6 +1631,7 @@ int ged_solve_batch(const ged_solve_desc *d, const ged_solve_out *o, void *strea
     prm.edit_u = d->edit_u;
     prm.edit_v = d->edit_v;
     prm.score_adj1 = d->score_adj1;
+    prm.score_ld = d->score_adj1_ld;
     prm.score_adj1_off = d->score_adj1_off;
     prm.score_idx = d->score_idx;
     prm.max_iter = d->max_iter;

@@ -190,7 +190,8 @@ class PairSet:
             self.num_pairs, p(self.n1, _lib.c_i32p), p(self.n2, _lib.c_i32p),
             p(self.adj1, _lib.c_u8p), p(self.adj1_off, _lib.c_i64p), p(self.adj2, _lib.c_u8p), p(self.adj2_off, _lib.c_i64p),
             p(self.lab1, _lib.c_i32p), p(self.lab1_off, _lib.c_i64p), p(self.lab2, _lib.c_i32p), p(self.lab2_off, _lib.c_i64p),
-            p(self.node_cost, _lib.c_f32p), p(self.node_cost_off, _lib.c_i64p), self.max_n1, self.max_n2)
+            p(self.node_cost, _lib.c_f32p), p(self.node_cost_off, _lib.c_i64p), self.max_n1, self.max_n2,
+            int(getattr(self, "adj1_ld", 0)), int(getattr(self, "adj2_ld", 0)))
 
     @property
     def mat_stride(self) -> int:

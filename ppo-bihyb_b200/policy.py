@@ -30,6 +30,12 @@ class DenseGraphBatch:
         self.x, self.adj, self.mask, self.num_nodes = x, adj, mask, num_nodes
 
     @staticmethod
+    def cat(batches: Sequence["DenseGraphBatch"]) -> "DenseGraphBatch":
+        """Concatenate along the batch dimension (all padded to the same node count: snapshots of one device state)."""
+        return DenseGraphBatch(torch.cat([b.x for b in batches]), torch.cat([b.adj for b in batches]),
+                               torch.cat([b.mask for b in batches]), torch.cat([b.num_nodes for b in batches]))
+
+    @staticmethod
     def from_data_list(graphs: Sequence, device) -> "DenseGraphBatch":
         B = len(graphs)
         ns = [int(g.x.shape[0]) for g in graphs]

@@ -84,7 +84,10 @@ class PPO:
         discounted = state_values
         rewards = []
         for reward, is_terminal in zip(reversed(memory.rewards), reversed(memory.is_terminals)):
-            reward = torch.as_tensor([float(r) for r in reward], dtype=torch.float32, device=self.device)
+            if torch.is_tensor(reward):          # device-resident rollout: one [B] tensor per time step
+                reward = reward.to(device=self.device, dtype=torch.float32)
+            else:
+                reward = torch.as_tensor([float(r) for r in reward], dtype=torch.float32, device=self.device)
             term = torch.as_tensor([float(t) for t in is_terminal], dtype=torch.float32, device=self.device)
             discounted = reward + self.gamma * (discounted * (1 - term))
             rewards.insert(0, discounted)
@@ -104,12 +107,16 @@ class PPO:
     def update(self, memory) -> torch.Tensor:
         """``PPO.update`` (ged_ppo_bihyb_train.py:158-221).  Returns the mean critic loss of the K epochs."""
         rewards = self._normalise(self._discounted_rewards(memory))
-        old_graph_1, old_graph_2 = [], []
-        for state in memory.states:
-            old_graph_1 += state[0]
-            old_graph_2 += state[1]
-        old_graph_1 = DenseGraphBatch.from_data_list(old_graph_1, self.device)      # padded once, evaluated K times
-        old_graph_2 = DenseGraphBatch.from_data_list(old_graph_2, self.device)
+        if isinstance(memory.states[0][0], DenseGraphBatch):     # device-resident rollout: snapshots of the dense batches
+            old_graph_1 = DenseGraphBatch.cat([state[0] for state in memory.states])
+            old_graph_2 = DenseGraphBatch.cat([state[1] for state in memory.states])
+        else:
+            old_graph_1, old_graph_2 = [], []
+            for state in memory.states:
+                old_graph_1 += state[0]
+                old_graph_2 += state[1]
+            old_graph_1 = DenseGraphBatch.from_data_list(old_graph_1, self.device)      # padded once, evaluated K times
+            old_graph_2 = DenseGraphBatch.from_data_list(old_graph_2, self.device)
         old_actions = torch.cat(memory.actions, dim=1).to(self.device)
         old_logprobs = torch.cat(memory.logprobs, dim=1).to(self.device).detach()
         critic_loss_sum = 0
@@ -157,4 +164,29 @@ def rollout_episode(ppo: PPO, env, tuples: Sequence, memory: Memory, max_timeste
         if timestep % update_timestep == 0:
             losses.append(ppo.update(memory))
             memory.clear_memory()
+    return timestep, total, losses
+
+
+def rollout_episode_device(ppo: PPO, state, greedy: torch.Tensor, memory: Memory, max_timesteps: int, timestep: int,
+                           update_timestep: int):
+    """:func:`rollout_episode` on a :class:`device_env.DeviceGEDState`: the graphs, the actions, the rewards and the PPO memory
+    stay on the device and nothing synchronises -- the policy forward reads the state's dense batches, ``state.step`` is one
+    solver call plus the in-place edge toggles.  ``state`` is the episode's start (left untouched); ``greedy`` [B] are the
+    solutions of the unedited pairs.  Returns (new timestep, summed reward per pair [B] on the device, critic losses)."""
+    st = state.clone()
+    greedy = greedy.to(st.device, torch.float32)
+    total = torch.zeros(len(st), device=st.device)
+    losses = []
+    for t in range(max_timesteps):
+        timestep += 1
+        with torch.no_grad():
+            actions = ppo.policy_old.act(st.batch1(), st.batch2(), memory)
+        rewards, greedy = st.step(actions, greedy)
+        memory.rewards.append(rewards)
+        memory.is_terminals.append([t == max_timesteps - 1] * len(st))
+        total += rewards
+        if timestep % update_timestep == 0:
+            losses.append(ppo.update(memory))
+            memory.clear_memory()
+    state.status |= st.status
     return timestep, total, losses

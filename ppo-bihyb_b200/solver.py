@@ -97,7 +97,7 @@ def solve_batch(pairs: PairSet, base_idx=None, edit_u=None, edit_v=None, solver:
                 x_init: Optional[torch.Tensor] = None, dense_x: bool = False, trace: bool = False,
                 check: bool = False, score_adj1: Optional[torch.Tensor] = None,
                 score_adj1_off: Optional[torch.Tensor] = None, score_idx=None, size_classes: bool = True,
-                plan=None) -> SolveResult:
+                plan=None, score_adj1_ld: int = 0) -> SolveResult:
     """All candidate solves of one batch (``ged_solve_batch``): one launch per size class, concurrently on side
     streams, results in candidate order.
 
@@ -154,7 +154,7 @@ def solve_batch(pairs: PairSet, base_idx=None, edit_u=None, edit_v=None, solver:
     p = _lib.ptr
     desc = _lib.GedSolveDesc(pairs.c_struct(), B, p(base_idx, _lib.c_i32p), p(edit_u, _lib.c_i32p), p(edit_v, _lib.c_i32p),
                              p(score_adj1, _lib.c_u8p), p(score_adj1_off, _lib.c_i64p), p(score_idx, _lib.c_i32p),
-                             int(max_iter), SOLVERS[solver], p(x_init, _lib.c_f32p), ms, p(workspace, _lib.c_f32p),
+                             int(score_adj1_ld), int(max_iter), SOLVERS[solver], p(x_init, _lib.c_f32p), ms, p(workspace, _lib.c_f32p),
                              p(locks, _lib.c_i32p), 0, 0, p(None, _lib.c_i32p), 0, p(None, _lib.c_i32p))
 
     def set_region(k):

@@ -16,6 +16,7 @@ import torch
 import torch.distributed as dist
 from ppo_bihyb_b200 import ppo as ppo_mod
 from ppo_bihyb_b200 import synthetic
+from ppo_bihyb_b200.device_env import DeviceGEDState
 from ppo_bihyb_b200.ged_env import GEDenv
 from ppo_bihyb_b200.graphs import Data
 
@@ -24,6 +25,7 @@ ap.add_argument("--config", default="aids-20-30")
 ap.add_argument("--pairs", type=int, default=64)
 ap.add_argument("--episodes", type=int, default=2)
 ap.add_argument("--max-timesteps", type=int, default=10)
+ap.add_argument("--host-state", action="store_true", help="roll out through GEDenv.step_batch on lists of Data graphs instead of the device-resident state")
 args = ap.parse_args()
 world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
@@ -39,6 +41,17 @@ g1 = [Data.from_host(a, dev) for a, _ in pairs]
 g2 = [Data.from_host(b, dev) for _, b in pairs]
 geds, ks, _ = env.solve_feasible_ged_batch(g1, g2, "ipfp")
 tuples = [(a, b, k, float(g)) for a, b, k, g in zip(g1, g2, ks, geds)]
+state = None if args.host_state else DeviceGEDState(env, g1, g2)
+greedy0 = torch.cat(geds)
+
+
+def episode(timestep):
+    if state is None:
+        timestep, total, losses = ppo_mod.rollout_episode(ppo, env, tuples, memory, args.max_timesteps, timestep, args.max_timesteps)
+        return timestep, sum(total) / len(total)
+    timestep, total, losses = ppo_mod.rollout_episode_device(ppo, state, greedy0, memory, args.max_timesteps, timestep, args.max_timesteps)
+    return timestep, total.mean()            # stays on the device until the end of the timed region
+
 memory = ppo_mod.Memory()
 timestep = 0
 t_update = 0.0
@@ -46,28 +59,35 @@ orig_update = ppo.update
 
 
 def timed_update(mem):
-    global t_update
-    torch.cuda.synchronize()
-    t = time.time()
+    # CUDA events, not synchronisation: the device-resident rollout never waits for the GPU inside an episode
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     out = orig_update(mem)
-    torch.cuda.synchronize()
-    t_update += time.time() - t
+    e1.record()
+    update_events.append((e0, e1))
     return out
 
 
+update_events = []
 ppo.update = timed_update
-timestep, _, _ = ppo_mod.rollout_episode(ppo, env, tuples, memory, args.max_timesteps, timestep, args.max_timesteps)   # warm-up
-t_update = 0.0
+timestep, _ = episode(timestep)   # warm-up
+torch.cuda.synchronize()
+update_events.clear()
 if world > 1:
     dist.barrier()
 torch.cuda.synchronize()
 t0 = time.time()
 rewards = []
 for _ in range(args.episodes):
-    timestep, total, losses = ppo_mod.rollout_episode(ppo, env, tuples, memory, args.max_timesteps, timestep, args.max_timesteps)
-    rewards.append(sum(total) / len(total))
+    timestep, mean_reward = episode(timestep)
+    rewards.append(mean_reward)
 torch.cuda.synchronize()
-dt = torch.tensor([time.time() - t0, t_update], device=dev)
+wall = time.time() - t0
+rewards = [float(r) for r in rewards]
+if state is not None:
+    state.raise_on_error()
+t_update = sum(a.elapsed_time(b) for a, b in update_events) * 1e-3        # GPU time between the update's first and last kernel
+dt = torch.tensor([wall, t_update], device=dev)
 if world > 1:
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     flat = torch.cat([p.detach().reshape(-1) for p in ppo.policy.parameters()])
@@ -79,7 +99,7 @@ else:
 if rank == 0:
     steps = args.episodes * args.max_timesteps * args.pairs * world
     print(json.dumps({"metric": "ppo_bihyb_ged_env_steps_per_sec", "value": steps / float(dt[0]), "n_gpus": world, "config": args.config,
-                      "pairs_per_gpu": args.pairs, "episodes": args.episodes, "max_timesteps": args.max_timesteps, "k_epochs": 10,
+                      "state": "host lists" if args.host_state else "device resident", "pairs_per_gpu": args.pairs, "episodes": args.episodes, "max_timesteps": args.max_timesteps, "k_epochs": 10,
                       "seconds": float(dt[0]), "update_seconds": float(dt[1]), "rollout_seconds": float(dt[0] - dt[1]),
                       "mean_episode_reward": rewards, "parameters_identical_across_ranks": in_sync}))
 if world > 1:
