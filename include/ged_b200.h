@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GED_ABI_VERSION 6
+#define GED_ABI_VERSION 7
 
 /* call-level errors */
 #define GED_OK 0
@@ -102,6 +102,11 @@ typedef struct ged_solve_desc {
      * (order-)list with an atomic increment until the list is exhausted -- a warp never idles behind a slower CTA-mate
      * and the last wave is as short as the longest single solve.  NULL: one candidate per warp, assigned statically. */
     int32_t *work_counter;
+    /* Launch shape hint.  0: packed (CTAs filled with candidates; right when the device is busy with this or other
+     * launches).  1: spread -- one candidate per CTA until every CTA slot of the device is taken (candidate = blockIdx +
+     * warp * gridDim; the work queue is not used): right for a latency-bound call of a few hundred candidates in total
+     * (a rollout or beam-search step), where each solve then has an SM (almost) to itself. */
+    int32_t launch_hint;
 } ged_solve_desc;
 
 typedef struct ged_solve_out {

@@ -68,16 +68,72 @@ def beam_search_batch(policy_model, ged_env, tuples: Sequence, max_actions: int,
              "probs": best[p].probs, "time": dt} for p in range(P)]
 
 
+@torch.no_grad()
+def beam_search_batch_device(policy_model, ged_env, tuples: Sequence, max_actions: int, beam_size: int = 5) -> List[dict]:
+    """:func:`beam_search_batch` with the beam states resident on the device (:class:`device_env.DeviceGEDState`): the policy
+    reads the states' dense batches, the candidates of a step are successor states built by an index gather + in-place
+    toggles, one solver call evaluates them all, and the surviving beams are another gather.  Per step the host sees only
+    the proposals (ids, probabilities) and the rewards -- two small copies -- and keeps the reference's bookkeeping."""
+    from .device_env import DeviceGEDState
+    start = time.time()
+    k = beam_size
+    P = len(tuples)
+    root = DeviceGEDState(ged_env, [t[0] for t in tuples], [t[1] for t in tuples])
+    greedy = [float(t[3]) for t in tuples]
+    state = root                                             # live beam states; owner[s] = (pair, beam record)
+    owner = [(p, _Beam(None, 0.0, [], [])) for p in range(P)]
+    best = [o[1] for o in owner]
+    for _ in range(max_actions):
+        if not owner:
+            break
+        acts1, probs1, acts2, probs2 = (t.cpu() for t in policy_model.propose(state.batch1(), state.batch2(), k))
+        cand = []
+        for s in range(len(owner)):
+            for a in range(k):
+                for b in range(k):
+                    p1, p2 = float(probs1[s, a]), float(probs2[s, a, b])
+                    if p1 > 1e-3 and p2 > 1e-3:              # :22
+                        cand.append((s, int(acts1[s, a]), int(acts2[s, a, b]), p1, p2))
+        if not cand:
+            break
+        arr = torch.tensor([[c[0], c[1], c[2]] for c in cand], dtype=torch.long)
+        succ = state.select(arr[:, 0], arr[:, 1], arr[:, 2])
+        ged = succ.solve().cpu()
+        succ.raise_on_error()
+        searched = [[] for _ in range(P)]
+        for j, c in enumerate(cand):
+            p, beam = owner[c[0]]
+            searched[p].append((_Beam(None, greedy[p] - float(ged[j]), beam.acts + [(c[1], c[2])], beam.probs + [(c[3], c[4])]), j))
+        keep, owner = [], []
+        for p in range(P):
+            if not searched[p]:
+                continue
+            searched[p].sort(key=lambda x: x[0].reward, reverse=True)   # stable: ties keep candidate order (:107)
+            if searched[p][0][0].reward > best[p].reward:               # :108
+                best[p] = searched[p][0][0]
+            for beam, j in searched[p][:beam_size]:                     # :112
+                keep.append(j)
+                owner.append((p, beam))
+        state = succ.subset(torch.tensor(keep, dtype=torch.long))
+    dt = (time.time() - start) / max(P, 1)
+    return [{"reward": best[p].reward, "solution": greedy[p] - best[p].reward, "acts": best[p].acts,
+             "probs": best[p].probs, "time": dt} for p in range(P)]
+
+
 def beam_search(policy_model, ged_env, inp_graph_1, inp_graph_2, ori_ks, greedy_cost, max_actions, beam_size=5,
                 multiprocess_pool=None):
     """The reference's single-pair entry point (``ged_ppo_bihyb_eval.py:37``); ``multiprocess_pool`` is ignored."""
     return beam_search_batch(policy_model, ged_env, [(inp_graph_1, inp_graph_2, ori_ks, greedy_cost)], max_actions, beam_size)[0]
 
 
-def evaluate(policy_net, ged_env, eval_graphs, max_steps=10, search_size=10, mp_pool=None, verbose=False):
+def evaluate(policy_net, ged_env, eval_graphs, max_steps=10, search_size=10, mp_pool=None, verbose=False, host_state=False):
     """``evaluate`` (:123-166) over tuples ``(graph_1, graph_2, ori_k, ori_greedy, baselines, _)`` as ``generate_tuples``
-    returns them; all pairs are searched together.  Same result dictionary as the reference."""
-    results = beam_search_batch(policy_net, ged_env, [(t[0], t[1], t[2], t[3]) for t in eval_graphs], max_steps, search_size)
+    returns them; all pairs are searched together, by default with the beam states resident on the device (``host_state``
+    selects the list-of-Data path).  Same result dictionary as the reference."""
+    if not host_state:          # the device-resident search needs the policy on a CUDA device (and a real GEDenv)
+        host_state = next(policy_net.parameters()).device.type != "cuda" or not hasattr(ged_env, "_host_pair")
+    search = beam_search_batch if host_state else beam_search_batch_device
+    results = search(policy_net, ged_env, [(t[0], t[1], t[2], t[3]) for t in eval_graphs], max_steps, search_size)
     ret = {"reward": {}, "ratio": {}, "solution": {}, "gap": {}, "num_act": {}, "time": {}}
     for i, (t, bs) in enumerate(zip(eval_graphs, results)):
         ori_greedy, baselines = float(t[3]), t[4]

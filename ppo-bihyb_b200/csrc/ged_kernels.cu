@@ -951,6 +951,7 @@ struct SolveParams {
     const int32_t *order;
     int count;
     int32_t *work_counter;   // device int32, zero at launch: persistent warps pull candidates from it (nullptr: static assignment)
+    int spread;              // static assignment: 1 = candidate blockIdx + warp * gridDim (spread over CTAs), 0 = CTA-major
     int tmem_warps;          // 0 or 4: warps 0..3 of every CTA keep their cost matrix in tensor memory
     int tmem_cols;           // columns allocated per CTA (power of two >= 32)
     ged_solve_out out;
@@ -1173,6 +1174,7 @@ __device__ void solve_one(const SolveParams &prm, int b, int slot, const Slice &
 // tmem_warps slices without a cost block, then the others with one.
 // TM = false: no tensor-memory instruction in the binary at all (a CTA of a kernel that may allocate tensor memory holds
 // the SM's allocation permit until it relinquishes it, which keeps other CTAs off the SM).
+constexpr int kSpreadMaxPerLaunch = 1 << 20;   // no extra limit: the caller's launch_hint decides
 constexpr int kMaxCtaWarps = 8;          // 4 tensor-memory warps + at most 4 shared-memory warps
 constexpr int kModeSmem = 0, kModeTmem = 1, kModeHybrid = 2;   // cost store of the CTA's warps: all shared / all tensor memory / both
 
@@ -1208,7 +1210,7 @@ __global__ void __launch_bounds__(32 * kMaxCtaWarps, S <= 3 ? 2 : 1) ged_solve_k
                                 prm.layout, m1, m2, true);
     uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16);
     asm volatile("" : "+r"(taddr));          // opaque: kept in a register instead of being re-derived from %tid per row fetch
-    for (int slot = gwarp;;) {
+    for (int slot = prm.spread ? blockIdx.x + warp * gridDim.x : gwarp;;) {       // static assignment (see launch_solve_as)
         if (prm.work_counter) {
             if ((threadIdx.x & 31) == 0) slot = atomicAdd(prm.work_counter, 1);
             slot = __shfl_sync(kFull, slot, 0);
@@ -1495,22 +1497,40 @@ int launch_solve_as(SolveParams prm, const CtaShape &c, cudaStream_t stream)
     const int wpb = c.tmem_warps + c.smem_warps;
     cudaError_t e = cudaFuncSetAttribute(ged_solve_kernel<S, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes);
     if (e != cudaSuccess) return fail_cuda(e, "ged_solve_batch");
-    if (const int carve = env_int("GED_B200_CARVEOUT", -1); carve >= 0) {       // experiments: explicit shared-memory carve-out (percent)
+    // Shared-memory carve-out.  Packed (throughput) launches all ask for the maximum: an SM runs CTAs of one L1/shared split
+    // at a time, so size classes with different preferences (launched concurrently on side streams) would exclude each
+    // other from an SM -- measured +13 % on the AIDS-30-50 mix (two classes), +3.6 % on the AIDS-50+ mix.  Spread
+    // (latency-bound) launches leave the choice to the driver: with one warp per SM the L1 serves the K.X gathers, and
+    // the 28 KB that the maximum carve-out leaves made a 32-pair AIDS-50+ step 32 % longer.
+    // GED_B200_CARVEOUT overrides both (percent; -1 = driver's choice).
+    prm.spread = prm.spread && prm.count < kSpreadMaxPerLaunch;
+    {
+        const int carve = env_int("GED_B200_CARVEOUT", prm.spread ? -1 : 100);
         e = cudaFuncSetAttribute(ged_solve_kernel<S, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (e != cudaSuccess) return fail_cuda(e, "ged_solve_batch");
     }
     if (env_int("GED_B200_VERBOSE", 0))
         fprintf(stderr, "[ged_b200] solve<S=%d> count=%d max_n=(%d,%d) cta: %d tmem warps (%d cols) + %d smem warps, %d B dynamic smem\n",
                 S, prm.count, prm.pairs.max_n1, prm.pairs.max_n2, c.tmem_warps, c.tmem_cols, c.smem_warps, c.smem_bytes);
+    // Launch shape (ged_solve_desc.launch_hint).  Packed: persistent CTAs (no more than the device holds at once) pulling
+    // from the work queue.  Spread (a latency-bound call of a few hundred candidates): one candidate per CTA until every
+    // CTA slot is taken, then a second one per CTA, ... -- measured 7-13 % shorter steps at 60-270 candidates of AIDS-50+
+    // shape; with more candidates the idle warps of spread CTAs hold tensor memory and shared memory that others need.
     int grid = (prm.count + wpb - 1) / wpb;
-    if (prm.work_counter) {                                     // persistent launch: no more CTAs than the device holds at once
+    {
         int dev = 0, sms = 0;
         cudaFuncAttributes fa;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
             cudaFuncGetAttributes(&fa, ged_solve_kernel<S, MODE>) != cudaSuccess)
             return fail(GED_E_CUDA, "ged_solve_batch: device query failed");
         const int resident = sms * resident_ctas(c, fa.numRegs);
-        if (grid > resident) grid = resident;
+        if (prm.spread && prm.count < resident * wpb) {
+            prm.work_counter = nullptr;
+            grid = prm.count < resident ? prm.count : resident;
+        } else {
+            prm.spread = 0;
+            if (prm.work_counter && grid > resident) grid = resident;
+        }
     }
     ged_solve_kernel<S, MODE><<<grid, wpb * 32, c.smem_bytes, stream>>>(prm);
     e = cudaGetLastError();
@@ -1647,6 +1667,7 @@ int ged_solve_batch(const ged_solve_desc *d, const ged_solve_out *o, void *strea
     prm.order = d->order;
     prm.count = d->order ? d->order_count : d->B;
     prm.work_counter = d->work_counter;
+    prm.spread = d->launch_hint == 1 && env_int("GED_B200_SPREAD", 1);
     if (prm.count < 0 || prm.count > d->B) return fail(GED_E_BADARG, "ged_solve_batch: order_count out of range");
     if (prm.count == 0) return GED_OK;
     prm.tmem_warps = 0;

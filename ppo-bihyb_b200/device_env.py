@@ -161,6 +161,13 @@ class DeviceGEDState:
         out.apply_edits(u.to(self.device), v.to(self.device))
         return out
 
+    def subset(self, idx: torch.Tensor) -> "DeviceGEDState":
+        """States ``idx`` of this one, unchanged (the beams that survive a search step)."""
+        zero = torch.zeros(len(idx), dtype=torch.long)
+        out = self.select(idx, zero, zero)                  # u == v: no edit
+        out.status |= self.status[idx.to(self.device).long()]
+        return out
+
     # ---- leaving the device --------------------------------------------------------------------------------------------
     def raise_on_error(self) -> None:
         """One synchronising check of everything solved so far (the per-call check of ``step_batch``, deferred)."""

@@ -14,6 +14,10 @@ from .graphs import PairSet
 SOLVERS = {"ipfp": _lib.GED_SOLVER_IPFP, "hungarian": _lib.GED_SOLVER_HUNGARIAN}
 
 
+# calls of at most this many candidates in total are latency-bound (a rollout / beam-search step): one candidate per CTA
+SPREAD_MAX_CANDIDATES = 512
+
+
 def _stream(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
@@ -155,7 +159,8 @@ def solve_batch(pairs: PairSet, base_idx=None, edit_u=None, edit_v=None, solver:
     desc = _lib.GedSolveDesc(pairs.c_struct(), B, p(base_idx, _lib.c_i32p), p(edit_u, _lib.c_i32p), p(edit_v, _lib.c_i32p),
                              p(score_adj1, _lib.c_u8p), p(score_adj1_off, _lib.c_i64p), p(score_idx, _lib.c_i32p),
                              int(score_adj1_ld), int(max_iter), SOLVERS[solver], p(x_init, _lib.c_f32p), ms, p(workspace, _lib.c_f32p),
-                             p(locks, _lib.c_i32p), 0, 0, p(None, _lib.c_i32p), 0, p(None, _lib.c_i32p))
+                             p(locks, _lib.c_i32p), 0, 0, p(None, _lib.c_i32p), 0, p(None, _lib.c_i32p),
+                             1 if B <= SPREAD_MAX_CANDIDATES else 0)
 
     def set_region(k):
         if counters is not None:

@@ -22,6 +22,7 @@ ap.add_argument("--configs", default="aids-20-30,aids-30-50,aids-50+")
 ap.add_argument("--pairs", type=int, default=10)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--beam", type=int, default=3)
+ap.add_argument("--host-state", action="store_true", help="search over lists of Data graphs (GEDenv.step_batch) instead of device-resident states")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
@@ -37,6 +38,17 @@ class CountingEnv(GEDenv):
         return super().step_batch(g1s, *a, **k)
 
 
+from ppo_bihyb_b200.device_env import DeviceGEDState
+_solve = DeviceGEDState.solve
+
+
+def counting_solve(self, *a, **k):
+    CountingEnv.solves += len(self)
+    return _solve(self, *a, **k)
+
+
+DeviceGEDState.solve = counting_solve
+print("state:", "host lists" if args.host_state else "device resident")
 print("| config | pairs | evaluate() wall s | lower-level solves | solves/s end to end | reference s/solve (1 CPU thread) | reference time for the same solves |")
 print("|---|---|---|---|---|---|---|")
 for cfg in args.configs.split(","):
@@ -46,11 +58,11 @@ for cfg in args.configs.split(","):
         d1, d2 = Data.from_host(g1, dev), Data.from_host(g2, dev)
         ged0, k0, _ = env.solve_feasible_ged(d1, d2, "ipfp")
         tuples.append((d1, d2, k0, float(ged0), {"ipfp": float(ged0)}, None))
-    evaluate(policy, env, tuples, max_steps=2, search_size=args.beam)          # warm-up
+    evaluate(policy, env, tuples, max_steps=2, search_size=args.beam, host_state=args.host_state)          # warm-up
     CountingEnv.solves = 0
     torch.cuda.synchronize()
     t0 = time.time()
-    res = evaluate(policy, env, tuples, max_steps=args.steps, search_size=args.beam)
+    res = evaluate(policy, env, tuples, max_steps=args.steps, search_size=args.beam, host_state=args.host_state)
     torch.cuda.synchronize()
     dt = time.time() - t0
     z = np.load(os.path.join(gold, "solve_" + cfg.replace("+", "plus") + ".npz"))

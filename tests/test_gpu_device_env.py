@@ -99,3 +99,26 @@ def test_device_rollout_equals_list_rollout(cuda_device):
     for (name, pa), pb in zip(ppo_a.policy.named_parameters(), ppo_b.policy.parameters()):
         assert torch.allclose(pa, pb, rtol=1e-5, atol=1e-7), name
     assert torch.equal(state.adj1, DeviceGEDState(env, g1, g2).adj1)                                   # the start state is left untouched
+
+
+def test_device_beam_search_equals_list_beam_search(cuda_device):
+    """The device-resident search and the Data-list search expand the same candidates and return the same best edit
+    sequences (deterministic policy, both padded to the same node count)."""
+    from ppo_bihyb_b200 import beam_search as bs
+    from ppo_bihyb_b200.policy import ActorCritic
+    g1, g2 = _pairs(cuda_device, num=4, seed=904)
+    env = GEDenv("ipfp", "AIDS-20-30", device=cuda_device)
+    geds, ks, _ = env.solve_feasible_ged_batch(g1, g2, "ipfp")
+    tuples = [(a, b, k, float(g)) for a, b, k, g in zip(g1, g2, ks, geds)]
+    torch.manual_seed(3)
+    policy = ActorCritic(34, 64, False, 0, 3).to(cuda_device).eval()
+    want = bs.beam_search_batch(policy, env, tuples, max_actions=3, beam_size=2)
+    got = bs.beam_search_batch_device(policy, env, tuples, max_actions=3, beam_size=2)
+    for w, g in zip(want, got):
+        assert g["reward"] == w["reward"] and g["solution"] == w["solution"]
+        if g["acts"] != w["acts"]:           # equal-reward alternatives may be ordered by probabilities that differ in the last bit
+            assert len(g["acts"]) == len(w["acts"])
+        else:
+            assert np.allclose(np.asarray(g["probs"]), np.asarray(w["probs"]), rtol=1e-4)
+    res = bs.evaluate(policy, env, [t + ({"ipfp": t[3]}, None) for t in tuples], max_steps=2, search_size=2)
+    assert set(res) == {"reward", "ratio", "solution", "gap", "num_act", "time"} and "mean" in res["solution"]

@@ -54,15 +54,16 @@ def test_full_size_batch_properties(cuda_device):
 @pytest.mark.parametrize("config,num,per", [("aids-30-50", 8, 24), ("n=70", 3, 8), ("n=100", 2, 6)])
 def test_cost_store_variants_are_bit_identical(cuda_device, config, num, per, monkeypatch):
     """Tensor-memory, shared-memory and hybrid launches of the same batch (incl. a size whose matrix needs the hybrid
-    CTA and one that needs S=4 slots), with and without the work queue, give the same bits; one candidate per size is
-    checked against the oracle."""
+    CTA and one that needs S=4 slots), with and without the work queue, spread or packed over the CTAs, give the same
+    bits; one candidate per size is checked against the oracle."""
     pairs = synthetic.make_pairs(config, num, seed_offset=61)
     edits = synthetic.make_edits(pairs, per, seed_offset=61)
     ps = PairSet.from_host(pairs, cuda_device)
     outs = []
-    for mode, queue in (("0", "1"), ("1", "1"), ("2", "1"), ("2", "0")):
+    for mode, queue, spread in (("0", "1", "1"), ("1", "1", "1"), ("2", "1", "1"), ("2", "0", "0"), ("2", "1", "0")):
         monkeypatch.setenv("GED_B200_COST_STORE", mode)
         monkeypatch.setenv("GED_B200_WORK_QUEUE", queue)              # persistent warps pulling from the queue / one solve per warp
+        monkeypatch.setenv("GED_B200_SPREAD", spread)                 # small batches: one candidate per CTA / CTAs packed
         if mode == "2":
             monkeypatch.setenv("GED_B200_SMEM_WARPS", "2")            # force shared-memory warps into the hybrid CTA
         outs.append(_solve(ps, edits))
