@@ -1475,8 +1475,10 @@ static CtaShape plan_cta(const SliceLayout &L, int max_n1, int S, int regs_per_t
     return c;
 }
 
-// CTAs of this shape one SM holds at once: shared memory (1 KB reserved per CTA), tensor-memory columns, registers, warps.
-// (The occupancy API counts a tensor-memory kernel as one CTA per SM, so this is computed by hand.)
+// CTAs of this shape one SM holds at once.  Tensor-memory kernels: by hand -- shared memory (1 KB reserved per CTA),
+// tensor-memory columns, warps, registers (allocated per CTA in units of 4 warps: ncu reports a 7-warp CTA at 136
+// registers as alone on its SM) -- because the occupancy API counts a tensor-memory kernel as one CTA per SM.
+// Shared-memory-only kernels: the occupancy API.
 static int resident_ctas(const CtaShape &c, int regs_per_thread)
 {
     const int wpb = c.tmem_warps + c.smem_warps;
@@ -1485,8 +1487,24 @@ static int resident_ctas(const CtaShape &c, int regs_per_thread)
     if (c.tmem_cols > 0) ctas = min(ctas, 512 / c.tmem_cols);
     ctas = min(ctas, 64 / wpb);
     const int regs = (regs_per_thread + 7) / 8 * 8;
-    if (regs > 0) ctas = min(ctas, 65536 / (regs * 32 * ((wpb + 3) / 4 * 4)));     // allocated in units of 4 warps
+    if (regs > 0) ctas = min(ctas, 65536 / (regs * 32 * ((wpb + 3) / 4 * 4)));
     return ctas < 1 ? 1 : ctas;
+}
+
+template <int S, int MODE>
+int resident_ctas_of(const CtaShape &c)
+{
+    const int wpb = c.tmem_warps + c.smem_warps;
+    if (cudaFuncSetAttribute(ged_solve_kernel<S, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes) != cudaSuccess) return -1;
+    if constexpr (MODE == kModeSmem) {
+        int ctas = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, ged_solve_kernel<S, MODE>, wpb * 32, c.smem_bytes) != cudaSuccess) return -1;
+        return ctas < 1 ? 1 : ctas;
+    } else {
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, ged_solve_kernel<S, MODE>) != cudaSuccess) return -1;
+        return resident_ctas(c, fa.numRegs);
+    }
 }
 
 template <int S, int MODE>
@@ -1519,11 +1537,10 @@ int launch_solve_as(SolveParams prm, const CtaShape &c, cudaStream_t stream)
     int grid = (prm.count + wpb - 1) / wpb;
     {
         int dev = 0, sms = 0;
-        cudaFuncAttributes fa;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-            cudaFuncGetAttributes(&fa, ged_solve_kernel<S, MODE>) != cudaSuccess)
+        const int per_sm = resident_ctas_of<S, MODE>(c);
+        if (per_sm < 0 || cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
             return fail(GED_E_CUDA, "ged_solve_batch: device query failed");
-        const int resident = sms * resident_ctas(c, fa.numRegs);
+        const int resident = sms * per_sm;
         if (prm.spread && prm.count < resident * wpb) {
             prm.work_counter = nullptr;
             grid = prm.count < resident ? prm.count : resident;
@@ -1578,7 +1595,9 @@ int GED_CAT(resident_solve_s, GED_TU_S)(const SliceLayout &L, int max_n1)
     const int regs = solve_regs<GED_TU_S>();
     if (regs < 0) return -1;
     const CtaShape c = plan_cta(L, max_n1, GED_TU_S, regs);
-    return resident_ctas(c, regs) * (c.tmem_warps + c.smem_warps);
+    const int wpb = c.tmem_warps + c.smem_warps;
+    if (c.tmem_warps > 0 && c.smem_warps > 0) return resident_ctas_of<GED_TU_S, kModeHybrid>(c) * wpb;
+    return (c.tmem_warps > 0 ? resident_ctas_of<GED_TU_S, kModeTmem>(c) : resident_ctas_of<GED_TU_S, kModeSmem>(c)) * wpb;
 }
 int GED_CAT(launch_lsape_s, GED_TU_S)(const LsapeParams &prm, cudaStream_t stream)
 {
