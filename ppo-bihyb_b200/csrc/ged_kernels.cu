@@ -14,10 +14,12 @@
 //   * TmemCost: in TENSOR MEMORY (tcgen05.st / tcgen05.ld, 32x32b shape): TMEM is 128 lanes x 512 columns of 32 bits
 //     per SM, each warp of a CTA owns one 32-lane quarter, element (i, a) sits at lane a & 31, column i * S + (a >> 5);
 //     a row of the matrix is ONE tcgen05.ld.  It is used purely as a second 256 KB scratchpad (no MMA): a hybrid CTA
-//     runs 4 TMEM-backed solves next to k shared-memory-backed ones, roughly doubling the solves in flight per SM.
+//     runs 4 TMEM-backed solves next to k shared-memory-backed ones (one instantiation for both, AnyCost).
 // The fractional IPFP iterate X and Y = X A2^T live in global memory (touched only between LAPs, L2 resident).
 // K is never built: K vec(X) is evaluated from the two bit-packed adjacency factors.  Warps never synchronise with each
 // other (the only CTA-wide barriers bracket the TMEM allocation).
+// Launches are persistent (as many CTAs as the device holds, warps pulling candidates from an atomic work queue) or, for
+// latency-bound calls of a few hundred candidates, spread one candidate per CTA (ged_solve_desc.launch_hint).
 //
 // All floating-point arithmetic follows the canonical order documented in oracle/ged_oracle.c (no FMA contraction:
 // explicit *_rn intrinsics, and the file is compiled with --fmad=false).
@@ -1172,9 +1174,8 @@ __device__ void solve_one(const SolveParams &prm, int b, int slot, const Slice &
 
 // CTA = [tmem_warps TMEM-backed solves][remaining warps: shared-memory-backed solves].  Dynamic shared memory:
 // tmem_warps slices without a cost block, then the others with one.
-// TM = false: no tensor-memory instruction in the binary at all (a CTA of a kernel that may allocate tensor memory holds
-// the SM's allocation permit until it relinquishes it, which keeps other CTAs off the SM).
-constexpr int kSpreadMaxPerLaunch = 1 << 20;   // no extra limit: the caller's launch_hint decides
+// MODE = kModeSmem: no tensor-memory instruction in the binary at all (a CTA of a kernel that may allocate tensor memory
+// holds the SM's allocation permit until it relinquishes it, which keeps other CTAs off the SM).
 constexpr int kMaxCtaWarps = 8;          // 4 tensor-memory warps + at most 4 shared-memory warps
 constexpr int kModeSmem = 0, kModeTmem = 1, kModeHybrid = 2;   // cost store of the CTA's warps: all shared / all tensor memory / both
 
@@ -1521,7 +1522,6 @@ int launch_solve_as(SolveParams prm, const CtaShape &c, cudaStream_t stream)
     // (latency-bound) launches leave the choice to the driver: with one warp per SM the L1 serves the K.X gathers, and
     // the 28 KB that the maximum carve-out leaves made a 32-pair AIDS-50+ step 32 % longer.
     // GED_B200_CARVEOUT overrides both (percent; -1 = driver's choice).
-    prm.spread = prm.spread && prm.count < kSpreadMaxPerLaunch;
     {
         const int carve = env_int("GED_B200_CARVEOUT", prm.spread ? -1 : 100);
         e = cudaFuncSetAttribute(ged_solve_kernel<S, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
