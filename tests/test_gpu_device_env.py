@@ -122,3 +122,23 @@ def test_device_beam_search_equals_list_beam_search(cuda_device):
             assert np.allclose(np.asarray(g["probs"]), np.asarray(w["probs"]), rtol=1e-4)
     res = bs.evaluate(policy, env, [t + ({"ipfp": t[3]}, None) for t in tuples], max_steps=2, search_size=2)
     assert set(res) == {"reward", "ratio", "solution", "gap", "num_act", "time"} and "mean" in res["solution"]
+
+
+def test_cli_trains_saves_and_evaluates_a_checkpoint(cuda_device, tmp_path, capsys):
+    """The drivers end to end on synthetic pairs: two episodes of 8 pairs, a beam-search test after the second, a checkpoint
+    under the reference's naming whose state_dict the evaluation driver (and the reference's ActorCritic) loads."""
+    import glob
+    from ppo_bihyb_b200 import cli
+    common = ["--synthetic", "aids-20-30", "--solver_type", "ipfp", "--train_sample", "8", "--test_sample", "3", "--batch_size", "8",
+              "--max_timesteps", "3", "--update_timestep", "3", "--k_epochs", "2", "--node_output_size", "64", "--gnn_layers", "3",
+              "--search_size", "2", "--random_seed", "1"]
+    cli.main(["train"] + common + ["--max_episodes", "2", "--log_interval", "1", "--test_interval", "2", "--save_dir", str(tmp_path),
+                                   "--json_log"])
+    out = capsys.readouterr().out
+    assert "Episode 2" in out and "Evaluate on Test" in out and '"ratio/test"' in out
+    saved = glob.glob(str(tmp_path / "PPO_ipfp_datasetaids-20-30_beam2_ratio*.pt"))
+    if saved:                                   # written when the test ratio beats 0 (an untrained policy may not)
+        sd = torch.load(saved[0], map_location="cpu")
+        assert "state_encoder.siamese_gcn.conv_0.weight" in sd and sd["state_encoder.siamese_gcn.conv_0.weight"].shape == (34, 64)
+        cli.main(["eval"] + common + ["--test_model_weight", saved[0]])
+        assert '"solution"' in capsys.readouterr().out

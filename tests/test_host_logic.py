@@ -1,4 +1,5 @@
 """CPU: host-side logic of the drop-in layer (packing, edge toggles, factor recovery, sharding arithmetic)."""
+import os
 import numpy as np
 import pytest
 import torch
@@ -130,3 +131,24 @@ def test_host_view_cache_follows_edge_toggles():
         assert np.array_equal(cached[0], want[0]) and np.array_equal(cached[1], want[1]), (step, u, v)
     d.edge_index[0, 0] = (d.edge_index[0, 0] + 1) % g.n            # in-place modification invalidates the view
     assert np.array_equal(data_to_host(d, synthetic.NUM_LABELS)[0], data_to_host(Data(x=d.x, edge_index=d.edge_index), synthetic.NUM_LABELS)[0])
+
+
+def test_cli_flags_and_yaml_overrides(tmp_path):
+    """The drivers keep the reference's flag names / defaults (ged_ppo_bihyb_train.py:397-431) and its YAML semantics: every
+    key overrides the flag of that name, an unknown key is an error (:440)."""
+    import importlib
+    cli = importlib.import_module("ppo_bihyb_b200.cli")
+    a = cli.parse_arguments(["train"])
+    assert (a.solver_type, a.dataset, a.gamma, a.k_epochs, a.update_timestep, a.max_timesteps) == ("hungarian", "AIDS700nef", 0.99, 4, 20, 300)
+    assert (a.learning_rate, a.eps_clip, a.node_output_size, a.gnn_layers, a.search_size, a.batch_size) == (0.002, 0.2, 16, 10, 5, 1)
+    assert a.betas == (0.9, 0.999) and a.lr_steps == [] and a.test_model_weight == "" and a.random_seed is None
+    cfg = tmp_path / "c.yaml"
+    cfg.write_text("solver_type: ipfp\ndataset: AIDS-30-50\nk_epochs: 10\nlr_steps: [100, 200]\nsearch_size: 3\n")
+    b = cli.parse_arguments(["eval", "--config", str(cfg), "--k_epochs", "2"])
+    assert (b.command, b.solver_type, b.dataset, b.k_epochs, b.lr_steps, b.search_size) == ("eval", "ipfp", "AIDS-30-50", 10, [100, 200], 3)
+    cfg.write_text("no_such_key: 1\n")
+    with pytest.raises(AssertionError, match="Unknown config key"):
+        cli.parse_arguments(["train", "--config", str(cfg)])
+    repo_cfg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "config", "ged_b200.yaml")
+    c = cli.parse_arguments(["train", "--config", repo_cfg])
+    assert (c.solver_type, c.dataset, c.max_timesteps, c.batch_size) == ("ipfp", "AIDS-20-30", 10, 64)
