@@ -1796,7 +1796,7 @@ int64_t ged_solve_smem_bytes(int32_t max_n1, int32_t max_n2)
 }
 
 int ged_abi_version(void) { return GED_ABI_VERSION; }
-const char *ged_version(void) { return "ged_b200 0.3.0 (sm_100a; canonical order v2; tensor-memory cost store)"; }
+const char *ged_version(void) { return "ged_b200 0.4.0 (sm_100a; ABI 7; canonical order v2; tensor-memory cost store; persistent work-queue launches)"; }
 const char *ged_last_error(void) { return g_err; }
 
 }  // extern "C"
