@@ -146,6 +146,13 @@ int ged_lsape_batch(int32_t B, const int32_t *n1, const int32_t *n2, int32_t max
  * x, cost and scratch hold one R x C matrix per pair at b * mat_stride; scratch receives X * A2^T. */
 int ged_kv_batch(const ged_pairs *pairs, const float *x, float *cost, float *scratch, int64_t mat_stride, void *stream);
 
+/* Replaces Sinkhorn(max_iter=iters, tau)(s, nrows, ncols) as rrwm_ged / ga_ged call it (utils/ged_env.py:434,468;
+ * utils/sinkhorn.py:143-239, log domain, non-batched branch) for B matrices at once: matrix b is rows[b] x cols[b] in the
+ * top-left corner of an ld_r x ld_c fp32 block at s + b * ld_r * ld_c; log_s = s / tau[b]; the passes alternate row (even)
+ * and column (odd) log-sum-exp normalisation over the whole matrix; out receives exp(log_s) inside the block, 0 outside. */
+int ged_sinkhorn_batch(int32_t B, const int32_t *rows, const int32_t *cols, int32_t ld_r, int32_t ld_c, const float *s,
+                       const float *tau, int32_t iters, float *out, void *stream);
+
 /* Replaces GEDenv.comp_ged (utils/ged_env.py:245-253) for binary x given as assignments: the coalesced edit-cost
  * reduction.  Candidate b scores (rowmatch_b, colmatch_b) on base pair base_idx[b] (identity if NULL). */
 int ged_score_batch(const ged_pairs *pairs, int32_t B, const int32_t *base_idx,

@@ -23,7 +23,7 @@ ABI_VERSION = 7
 
 # every symbol include/ged_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED_SYMBOLS = (
-    "ged_solve_batch", "ged_lsape_batch", "ged_kv_batch", "ged_score_batch", "ged_quadform_ws_elems",
+    "ged_solve_batch", "ged_lsape_batch", "ged_kv_batch", "ged_sinkhorn_batch", "ged_score_batch", "ged_quadform_ws_elems",
     "ged_quadform_dense_batch", "ged_limits", "ged_solve_smem_bytes", "ged_solve_max_resident", "ged_abi_version", "ged_version",
     "ged_last_error",
 )
@@ -105,6 +105,9 @@ def load():
     lib.ged_lsape_batch.restype = ctypes.c_int
     lib.ged_kv_batch.argtypes = [ctypes.POINTER(GedPairs), c_f32p, c_f32p, c_f32p, ctypes.c_int64, ctypes.c_void_p]
     lib.ged_kv_batch.restype = ctypes.c_int
+    lib.ged_sinkhorn_batch.argtypes = [ctypes.c_int32, c_i32p, c_i32p, ctypes.c_int32, ctypes.c_int32, c_f32p, c_f32p, ctypes.c_int32,
+                                       c_f32p, ctypes.c_void_p]
+    lib.ged_sinkhorn_batch.restype = ctypes.c_int
     lib.ged_score_batch.argtypes = [ctypes.POINTER(GedPairs), ctypes.c_int32, c_i32p, c_i32p, ctypes.c_int32,
                                     c_i32p, ctypes.c_int32, c_f32p, ctypes.c_void_p]
     lib.ged_score_batch.restype = ctypes.c_int

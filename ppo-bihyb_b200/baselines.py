@@ -83,6 +83,12 @@ class _Ragged:
         x[b.expand_as(cols)[ins], n1[:, None].expand_as(cols)[ins], cols[ins]] = 1.0
         return x
 
+    def sinkhorn(self, s: torch.Tensor, tau: torch.Tensor, iters: int) -> torch.Tensor:
+        """Log-domain Sinkhorn of every pair's matrix: the fused kernel (all passes in shared memory, one launch)."""
+        if not hasattr(self, "_sizes"):
+            self._sizes = (torch.from_numpy(self.R.astype(np.int32)).to(s.device), torch.from_numpy(self.C.astype(np.int32)).to(s.device))
+        return solver.sinkhorn_batch(s, self._sizes[0], self._sizes[1], tau.reshape(-1).expand(self.P), iters)
+
     def start(self) -> torch.Tensor:
         """``hungarian_ged`` of every pair (ged_env.py:303-305), padded 0/1."""
         res = solver.solve_batch(self.ps, solver="hungarian", check=True)
@@ -120,7 +126,7 @@ def rrwm_batch(ps: PairSet, max_iter: int = 100, sk_iter: int = 100, alpha: floa
         nv = rg.kv(v) * scale
         nv = nv / nv.abs().sum((1, 2), keepdim=True)
         tau = nv.amax((1, 2), keepdim=True) / beta
-        nv = alpha * _sinkhorn_log(-nv, valid, tau, sk_iter) + (1 - alpha) * last_v
+        nv = alpha * rg.sinkhorn(-nv, tau, sk_iter) + (1 - alpha) * last_v
         nv = nv * (1.0 / nv.abs().sum((1, 2), keepdim=True))
         v = torch.where(active[:, None, None], nv, last_v)
         iters += active.to(torch.int32)
@@ -147,7 +153,7 @@ def ga_batch(ps: PairSet, max_iter: int = 100, sk_iter: int = 10, tau0: float = 
         t = torch.full((rg.P, 1, 1), float(tau), device=dev)
         for _ in range(max_iter):
             last_v = v
-            nv = _sinkhorn_log(-rg.kv(v), valid, t, sk_iter)
+            nv = rg.sinkhorn(-rg.kv(v), t, sk_iter)
             v = torch.where(active[:, None, None], nv, last_v)
             active = active & ~(_l2(v - last_v) < 1e-4)
             if not bool(active.any()):

@@ -1404,6 +1404,65 @@ __global__ void ged_quadform_final_kernel(const float *partial, int ctas_per_mat
     out[b] = s;
 }
 
+// ---- log-domain Sinkhorn (the projection step of the RRWM / graduated-assignment baselines) -----------------------------
+// Reference utils/sinkhorn.py:143-239 (Sinkhorn.forward_log, non-batched branch): log_s = s / tau, then `iters` alternating
+// passes -- even: every row minus its log-sum-exp, odd: every column minus its log-sum-exp -- over the whole rows x cols
+// matrix, and exp at the end.  One CTA per matrix, the matrix in shared memory for all passes (odd pitch: the column pass
+// walks down a column with consecutive lanes), one warp per row / column, max-subtracted sums through warp shuffles.
+constexpr int kSinkhornThreads = 256;
+
+__device__ __forceinline__ float warp_max(float x)
+{
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) x = fmaxf(x, __shfl_xor_sync(kFull, x, off));
+    return x;
+}
+__device__ __forceinline__ float warp_sum(float x)
+{
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) x = __fadd_rn(x, __shfl_xor_sync(kFull, x, off));
+    return x;
+}
+
+__global__ void __launch_bounds__(kSinkhornThreads) ged_sinkhorn_kernel(const int32_t *rows, const int32_t *cols, int ld_r, int ld_c,
+                                                                       const float *__restrict__ s, const float *__restrict__ tau,
+                                                                       int iters, float *__restrict__ out, int pitch)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *m = reinterpret_cast<float *>(smem_raw);
+    const int b = blockIdx.x, R = rows[b], C = cols[b];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const float *src = s + (long long)b * ld_r * ld_c;
+    float *dst = out + (long long)b * ld_r * ld_c;
+    const float t = tau[b];
+    for (int e = threadIdx.x; e < R * C; e += blockDim.x) {
+        const int r = e / C, c = e - r * C;
+        m[r * pitch + c] = __fdiv_rn(src[r * ld_c + c], t);
+    }
+    __syncthreads();
+    for (int it = 0; it < iters; ++it) {
+        const bool by_row = (it & 1) == 0;
+        const int lines = by_row ? R : C, len = by_row ? C : R;
+        const int line_stride = by_row ? pitch : 1, elem_stride = by_row ? 1 : pitch;
+        for (int l = warp; l < lines; l += nwarps) {
+            float *p = m + l * line_stride;
+            float mx = -INFINITY;
+            for (int k = lane; k < len; k += 32) mx = fmaxf(mx, p[k * elem_stride]);
+            mx = warp_max(mx);
+            if (mx == -INFINITY) continue;               // an all -inf line stays as it is
+            float acc = 0.0f;
+            for (int k = lane; k < len; k += 32) acc = __fadd_rn(acc, expf(__fsub_rn(p[k * elem_stride], mx)));
+            const float lse = __fadd_rn(mx, logf(warp_sum(acc)));
+            for (int k = lane; k < len; k += 32) p[k * elem_stride] = __fsub_rn(p[k * elem_stride], lse);
+        }
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < ld_r * ld_c; e += blockDim.x) {
+        const int r = e / ld_c, c = e - r * ld_c;
+        dst[e] = (r < R && c < C) ? expf(m[r * pitch + c]) : 0.0f;
+    }
+}
+
 #endif  // !GED_TU_S
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1763,6 +1822,23 @@ int ged_quadform_dense_batch(int32_t B, int32_t nk, const float *k, int64_t k_st
     ged_quadform_final_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partial_ws, ctas, out, B);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(e, "ged_quadform_dense_batch");
+    return GED_OK;
+}
+
+int ged_sinkhorn_batch(int32_t B, const int32_t *rows, const int32_t *cols, int32_t ld_r, int32_t ld_c, const float *s,
+                       const float *tau, int32_t iters, float *out, void *stream)
+{
+    if (B < 0 || ld_r < 1 || ld_c < 1 || iters < 0) return fail(GED_E_BADARG, "ged_sinkhorn_batch: bad sizes");
+    if (B == 0) return GED_OK;
+    if (!rows || !cols || !s || !tau || !out) return fail(GED_E_BADARG, "ged_sinkhorn_batch: null pointer");
+    const int pitch = ld_c | 1;
+    const size_t smem = (size_t)ld_r * pitch * sizeof(float);
+    if (smem > (size_t)kMaxSmemBytes) return fail(GED_E_TOO_LARGE, "ged_sinkhorn_batch: matrix does not fit shared memory");
+    cudaError_t e = cudaFuncSetAttribute(ged_sinkhorn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail_cuda(e, "ged_sinkhorn_batch");
+    ged_sinkhorn_kernel<<<B, kSinkhornThreads, smem, (cudaStream_t)stream>>>(rows, cols, ld_r, ld_c, s, tau, iters, out, pitch);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(e, "ged_sinkhorn_batch");
     return GED_OK;
 }
 

@@ -273,6 +273,25 @@ def kv_batch(pairs: PairSet, x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def sinkhorn_batch(s: torch.Tensor, rows: torch.Tensor, cols: torch.Tensor, tau: torch.Tensor, iters: int) -> torch.Tensor:
+    """``Sinkhorn(max_iter=iters, tau)(s, nrows, ncols)`` (reference ``utils/sinkhorn.py:143-239``, log domain) for a padded
+    batch ``s`` [B, Rm, Cm] with per-matrix sizes ``rows`` / ``cols`` [B] and temperatures ``tau`` [B]: one launch, all passes
+    in shared memory.  Returns exp(log_s) inside every block, 0 in the padding."""
+    lib = _lib.require_cuda()
+    dev = s.device
+    s = s.to(torch.float32).contiguous()
+    B, Rm, Cm = s.shape
+    rows, cols = _as_i32(rows, dev), _as_i32(cols, dev)
+    tau = tau.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+    assert rows.numel() == cols.numel() == tau.numel() == B
+    out = torch.empty_like(s)
+    p = _lib.ptr
+    with torch.cuda.device(dev):
+        _lib.check(lib.ged_sinkhorn_batch(B, p(rows, _lib.c_i32p), p(cols, _lib.c_i32p), Rm, Cm, p(s, _lib.c_f32p), p(tau, _lib.c_f32p),
+                                          int(iters), p(out, _lib.c_f32p), _stream(dev)), "ged_sinkhorn_batch")
+    return out
+
+
 def score_batch(pairs: PairSet, rowmatch: torch.Tensor, colmatch: torch.Tensor, base_idx=None) -> torch.Tensor:
     """``comp_ged`` of binary solutions given as assignments (reference ``utils/ged_env.py:245-253``)."""
     lib = _lib.require_cuda()
