@@ -115,8 +115,12 @@ class GraphAttentionPooling(nn.Module):
 def log_sinkhorn(s, nrows, ncols, max_iter=20, tau=0.005):
     """``Sinkhorn.forward_log`` (utils/sinkhorn.py:143-239) with per-sample sizes, batched: entries outside a sample's
     nrows x ncols block stay at -inf (they contribute nothing to any logsumexp), iterations alternate row / column
-    normalisation starting with rows."""
+    normalisation starting with rows.  Without autograd on a CUDA device this is ``ged_sinkhorn_batch``."""
     B, n1, n2 = s.shape
+    if s.is_cuda and not torch.is_grad_enabled():
+        # inference (act / propose): the fused kernel -- all passes in shared memory, one launch instead of ~4 per pass
+        from . import solver
+        return solver.sinkhorn_batch(s, nrows, ncols, torch.full((B,), float(tau), device=s.device), max_iter)
     valid = (torch.arange(n1, device=s.device)[None, :, None] < nrows[:, None, None]) & \
             (torch.arange(n2, device=s.device)[None, None, :] < ncols[:, None, None])
     neg_inf = torch.full_like(s, -float("inf"))
