@@ -27,6 +27,9 @@ from .policy import DenseGraphBatch
 class DeviceGEDState:
     def __init__(self, env, graphs_1: Sequence, graphs_2: Sequence, score_graphs_1: Optional[Sequence] = None, device=None):
         _lib.require_cuda()
+        if env.solver_type not in solver.SOLVERS:
+            raise NotImplementedError(f"device-resident state runs the {sorted(solver.SOLVERS)} solvers; "
+                                      f"{env.solver_type!r} goes through GEDenv.step_batch")
         self.env = env
         dev = torch.device(device) if device is not None else env._dev(*(g.x for g in graphs_1))
         B = len(graphs_1)
