@@ -295,10 +295,12 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": extra.get("dram_bytes_per_launch"), "peak_source": which,
                          "algorithmic_bytes_per_step": alg, "kernel": "ged_solve_kernel",
-                         "note": "compute per byte is ~1e3 instructions: the kernel is bound by instruction issue and "
-                                 "shared-memory latency of the sequential LAP scan, not by HBM (DESIGN.md); the issue-slot "
-                                 "fraction from ncu is in `issue_active_pct`",
-                         "issue_active_pct": extra.get("issue_active_pct")},
+                         "note": "compute per byte is ~1e3 instructions: the kernel is bound by instruction issue of the "
+                                 "sequential LAP scan -- its busiest unit is the ALU pipe -- not by HBM (DESIGN.md); the ncu "
+                                 "figures of the dominant launch are in `issue_active_pct` and `binding_unit`",
+                         "issue_active_pct": extra.get("issue_active_pct"),
+                         "binding_unit": {"unit": "SM ALU pipe (sm__inst_executed_pipe_alu)", "pct_of_peak": extra.get("alu_pipe_pct"),
+                                          "fp64_pipe_pct": extra.get("fp64_pipe_active_pct"), "fma_pipe_pct": extra.get("fma_pipe_pct")}},
         }
         if not args.no_cpu_baseline and world == 1:      # reported at N=1 only
             threads = os.cpu_count() or 1
