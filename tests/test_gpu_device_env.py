@@ -142,3 +142,20 @@ def test_cli_trains_saves_and_evaluates_a_checkpoint(cuda_device, tmp_path, caps
         assert "state_encoder.siamese_gcn.conv_0.weight" in sd and sd["state_encoder.siamese_gcn.conv_0.weight"].shape == (34, 64)
         cli.main(["eval"] + common + ["--test_model_weight", saved[0]])
         assert '"solution"' in capsys.readouterr().out
+
+
+def test_cli_evaluates_on_a_gedlib_directory(cuda_device, tmp_path, capsys):
+    """The evaluation driver on a GEDLIB-style directory (synthetic .gxl files): dataset processing, tuple generation with
+    reference-format cache files, device-resident beam search."""
+    from _gxl import synthetic_raw_dir
+    from ppo_bihyb_b200 import cli
+    root = str(tmp_path / "gedlib")
+    synthetic_raw_dir(root)
+    cache = str(tmp_path / "cache")
+    cli.main(["eval", "--dataset", "AIDS-10-16", "--dataset_root", root, "--cache_dir", cache, "--solver_type", "ipfp",
+              "--train_sample", "4", "--test_sample", "3", "--max_timesteps", "2", "--search_size", "2",
+              "--node_output_size", "64", "--gnn_layers", "3", "--random_seed", "0"])
+    out = capsys.readouterr().out
+    assert "ipfp ged mean=" in out and "BEAMSEARCH" in out and '"solution"' in out
+    import os
+    assert sorted(os.listdir(cache)) == sorted(f"{s}_{n}_AIDS-10-16_{r}.pt" for s in ("hungarian", "ipfp", "rrwm") for n, r in ((4, 0), (3, 1)))
