@@ -112,9 +112,11 @@ def train(args):
     env, tuples_train, tuples_test = build_environment(args, device)
     args.node_feature_dim = env.feature_dim
     trainer = ppo_mod.PPO(_ppo_config(args), device)
-    if args.random_seed is not None:
-        torch.manual_seed(args.random_seed + 1000 * (rank + 1))                        # independent action sampling per rank
+    base_seed = args.random_seed if args.random_seed is not None else 0
+    torch.manual_seed(base_seed + 1000 * (rank + 1))                                   # independent action sampling per rank
     mine = tuples_train[rank::world] if world > 1 else tuples_train                   # every rank trains on its own slice
+    if len(mine) == 0:
+        raise ValueError(f'rank {rank} of {world} has no training tuples: train_sample={len(tuples_train)} < world size')
     memory = ppo_mod.Memory()
     best_test_ratio, running_reward, critic_loss, timestep = 0.0, 0.0, [], 0
     prev_time = time.time()

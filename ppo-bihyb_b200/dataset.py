@@ -274,9 +274,13 @@ def cache_path(cache_dir: str, solver: str, num_samples: int, dataset: str, rand
     return osp.join(cache_dir, f'{solver}_{num_samples}_{dataset}_{rand_id}.pt')
 
 
-def load_cache(path: str) -> Dict[str, Tuple[torch.Tensor, float]]:
-    """``{ 'i,j': (tensor([ged]), seconds) }`` as the reference writes it (ged_env.py:70-77)."""
-    return torch.load(path, map_location='cpu', weights_only=False)
+def load_cache(path: str, allow_pickle: bool = False) -> Dict[str, Tuple[torch.Tensor, float]]:
+    """``{ 'i,j': (tensor([ged]), seconds) }`` as the reference writes it (ged_env.py:70-77).
+
+    The format holds tensors, floats, tuples and a dict only, so the restricted unpickler (``weights_only=True``) reads
+    the reference's files and ours; a cache directory is shared state and must not be able to run code on load.
+    ``allow_pickle=True`` is the explicit opt-in for a file the restricted loader rejects."""
+    return torch.load(path, map_location='cpu', weights_only=not allow_pickle)
 
 
 def save_cache(path: str, result: Dict[str, Tuple[torch.Tensor, float]]) -> None:

@@ -51,23 +51,40 @@ def _default_device(*tensors):
 
 
 class _DenseKFactors:
-    """Factor view of a dense K handed in by reference-style callers (``ori_k`` tensors), cached per tensor."""
+    """Factor view of a dense K handed in by reference-style callers (``ori_k`` tensors), cached per tensor.
+
+    The key is the tensor's address, shape and version counter.  An address alone does not identify a tensor -- the
+    allocator hands a freed block to the next K of the same shape, and ``construct_k`` leaves every K at the same
+    version -- so each entry KEEPS the tensor it was derived from alive (its block cannot be handed out again while
+    the entry exists) and a hit is re-checked against the K in hand: its diagonal and the two adjacency slices must
+    still be the cached factors.  The cache is small (``_MAX`` entries, least recently used first out) because an
+    entry pins a dense K (55 MB at n=60)."""
     _cache = {}
+    _MAX = 4
+
+    @staticmethod
+    def _same_factors(k: torch.Tensor, n1: int, n2: int, val) -> bool:
+        a1, a2, cost = factors_from_dense_k(k, n1, n2)
+        if val is None:
+            return True            # "not of construct_k form" was decided on this very tensor (it is pinned by the entry)
+        return bool(np.array_equal(a1, val[0].adj) and np.array_equal(a2, val[1].adj) and np.array_equal(cost, val[2]))
 
     @classmethod
     def get(cls, k: torch.Tensor, n1: int, n2: int):
         key = (k.data_ptr(), tuple(k.shape), k._version, n1, n2)
         hit = cls._cache.get(key)
-        if hit is not None:
-            return hit
+        if hit is not None and cls._same_factors(k, n1, n2, hit[1]):
+            cls._cache[key] = cls._cache.pop(key)          # most recently used last
+            return hit[1]
         a1, a2, cost = factors_from_dense_k(k, n1, n2)
         ok = bool(np.all(a1 <= 1) and np.all(a2 <= 1) and np.array_equal(a1, a1.T) and np.array_equal(a2, a2.T))
         if ok:      # K must be exactly what construct_k builds from these factors (ged_env.py:213-226)
             ok = torch.equal(dense_k_from_factors(a1, a2, cost).to(k.device), k.to(torch.float32))
         val = (HostGraph(a1, np.zeros(n1, np.int32)), HostGraph(a2, np.zeros(n2, np.int32)), cost) if ok else None
-        if len(cls._cache) > 64:
-            cls._cache.clear()
-        cls._cache[key] = val
+        cls._cache.pop(key, None)
+        while len(cls._cache) >= cls._MAX:
+            cls._cache.pop(next(iter(cls._cache)))
+        cls._cache[key] = (k, val)
         return val
 
 
@@ -320,7 +337,8 @@ class GEDenv(object):
                 adj[v, u] = min(int(adj[v, u]) + 1, 255)
             ei = np.ascontiguousarray(ei)
             new_graph_1.edge_index = torch.from_numpy(ei).to(graph_1.edge_index.device, non_blocking=True)
-            new_graph_1._ged_host = (host_cache_key(new_graph_1, cached[0][5]), adj, cached[2], cached[3], ei)
+            new_graph_1._ged_host = (host_cache_key(new_graph_1, cached[0][5]), adj, cached[2], cached[3], ei,
+                                     (new_graph_1.edge_index, new_graph_1.x))
             return new_graph_1
         new_graph_1 = graph_1.clone()
         ei = new_graph_1.edge_index

@@ -73,7 +73,9 @@ def data_to_host(g, ori_feature_dim: int) -> Tuple[np.ndarray, Optional[np.ndarr
         labels = feat.argmax(1).astype(np.int32)
     out = (np.minimum(adj, 255).astype(np.uint8), labels, feat)
     if isinstance(g, Data):
-        g._ged_host = (key,) + out + (ei,)  # host view, valid while x / edge_index are the same (unmodified) tensors
+        # host view, valid while x / edge_index are the same (unmodified) tensors.  The entry keeps the two tensors alive:
+        # the key holds their addresses, and an address can only be handed out again once its tensor is freed.
+        g._ged_host = (key,) + out + (ei, (g.edge_index, g.x))
     return out
 
 

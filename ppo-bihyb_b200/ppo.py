@@ -107,6 +107,13 @@ class PPO:
     def update(self, memory) -> torch.Tensor:
         """``PPO.update`` (ged_ppo_bihyb_train.py:158-221).  Returns the mean critic loss of the K epochs."""
         rewards = self._normalise(self._discounted_rewards(memory))
+        if _distributed():              # the gradient mean below is the global-batch gradient only for equal shards
+            count = torch.tensor([float(rewards.numel())], device=self.device)
+            lo, hi = count.clone(), count.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            if float(lo) != float(hi):
+                raise ValueError(f'PPO.update: ranks hold different numbers of transitions ({int(lo)}..{int(hi)})')
         if isinstance(memory.states[0][0], DenseGraphBatch):     # device-resident rollout: snapshots of the dense batches
             old_graph_1 = DenseGraphBatch.cat([state[0] for state in memory.states])
             old_graph_2 = DenseGraphBatch.cat([state[1] for state in memory.states])

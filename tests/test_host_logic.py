@@ -152,3 +152,35 @@ def test_cli_flags_and_yaml_overrides(tmp_path):
     repo_cfg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "config", "ged_b200.yaml")
     c = cli.parse_arguments(["train", "--config", repo_cfg])
     assert (c.solver_type, c.dataset, c.max_timesteps, c.batch_size) == ("ipfp", "AIDS-20-30", 10, 64)
+
+
+def test_dense_k_factor_cache_does_not_alias_freed_tensors():
+    """Regression: same-shape dense Ks built and freed in a loop get the same address and version from
+    the allocator; the factor cache must never hand back an earlier K's factors."""
+    from ppo_bihyb_b200.ged_env import _DenseKFactors
+    rng = np.random.default_rng(5)
+    n1, n2 = 6, 7
+    _DenseKFactors._cache.clear()
+    seen_ptrs = set()
+    for rep in range(12):
+        a1 = np.triu((rng.random((n1, n1)) < 0.4).astype(np.uint8), 1)
+        a1 = a1 + a1.T
+        a2 = np.triu((rng.random((n2, n2)) < 0.4).astype(np.uint8), 1)
+        a2 = a2 + a2.T
+        cost = label_node_cost(rng.integers(0, 3, n1).astype(np.int32), rng.integers(0, 3, n2).astype(np.int32))
+        k = dense_k_from_factors(a1, a2, cost)
+        seen_ptrs.add(k.data_ptr())
+        fac = _DenseKFactors.get(k, n1, n2)
+        assert fac is not None
+        assert np.array_equal(fac[0].adj, a1) and np.array_equal(fac[1].adj, a2) and np.array_equal(fac[2], cost)
+        again = _DenseKFactors.get(k, n1, n2)               # a hit on the live tensor
+        assert again is fac
+        del k
+    assert len(_DenseKFactors._cache) <= _DenseKFactors._MAX
+    # an in-place edit of a cached K is a different K (version counter) and must be re-derived
+    k = dense_k_from_factors(a1, a2, cost)
+    f0 = _DenseKFactors.get(k, n1, n2)
+    k4 = k.view(n1 + 1, n2 + 1, n1 + 1, n2 + 1)
+    was = float(k4[0, n2, 1, n2])
+    k4[0, n2, 1, n2] = 1.0 - was            # breaks the symmetry of A1 -> not a construct_k matrix any more
+    assert _DenseKFactors.get(k, n1, n2) is None and f0 is not None
