@@ -66,17 +66,32 @@ def workload_name(args, world):
             f"({args.pairs * args.edits * world} candidate solves per step, interleaved over {world} GPU(s)), max_iter {args.max_iter}")
 
 
-# ---- CPU baseline: the oracle port on the box's host cores ----------------------------------------------------------
-def cpu_baseline(args, sample, threads):
-    """Times oracle/ged_oracle.c (the C restatement of the reference's path; `kind: port`) on a bounded sample of the
-    same workload, `threads` solves in flight (ctypes releases the GIL).  The reference itself is Python/torch/SciPy and
-    cannot travel to this box; its measured 1-thread times are recorded in BASELINE.md / DESIGN.md."""
+# ---- CPU arms: the reference itself (oracle/_ref, oracle/ref_runner.py) and the C port (oracle/ged_oracle.c) -------------
+def host_cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def sample_indices(n, count, phase=0):
+    """`count` candidate indices spread evenly over a batch of n; `phase` shifts the comb so that successive steps sample
+    different candidates of the same workload."""
+    return [int((n * (2 * t + 1) // (2 * count) + phase * 7919) % n) for t in range(count)]
+
+
+def cpu_port(args, sample, threads, phase=0):
+    """oracle/ged_oracle.c (the C restatement of the reference's path; `kind: port`) on a bounded sample of the workload,
+    `threads` solves in flight (ctypes releases the GIL)."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import ged_oracle as go
     from ppo_bihyb_b200.graphs import label_node_cost
     pairs, base, eu, ev = workload(args, 0)
     go.lib()
-    idx = [int(i) for i in (len(base) * (2 * t + 1) // (2 * sample) for t in range(sample))]   # spread over the batch
+    idx = sample_indices(len(base), sample, phase)
 
     def one(b):
         g1, g2 = pairs[base[b]]
@@ -89,32 +104,95 @@ def cpu_baseline(args, sample, threads):
     return len(idx) / dt, dt, idx, geds
 
 
+class ReferenceArm:
+    """The UNMODIFIED reference `GEDenv.step` (utils/ged_env.py:110-124) in a pool of `cores` worker processes, one torch
+    thread each -- the reference's own parallelism (ged_ppo_bihyb_train.py:259-260,294-295).  A step = `cores` candidates
+    of the workload, one per worker; ori_k of the base pair is built outside the timed part (generate_tuples does that
+    once per tuple, :83)."""
+
+    def __init__(self, args, cores):
+        from oracle import ref_runner
+        self.args, self.cores = args, cores
+        self.pairs, self.base, self.eu, self.ev = workload(args, 0)
+        self.pool = ref_runner.ReferencePool(cores)
+
+    def jobs(self, phase):
+        idx = sample_indices(len(self.base), self.cores, phase)
+        return idx, [(self.pairs[self.base[b]][0], self.pairs[self.base[b]][1], int(self.eu[b]), int(self.ev[b])) for b in idx]
+
+    def warm(self, steps):
+        """untimed: pool start-up, page-in, first-call costs -- the same code at max_iter 3"""
+        if steps <= 0:
+            return
+        self.pool.set_max_iter(3)
+        for w in range(steps):
+            self.pool.step(self.jobs(1000 + w)[1])
+        self.pool.set_max_iter(self.args.max_iter)
+
+    def step(self, phase):
+        idx, jobs = self.jobs(phase)
+        geds, wall, per = self.pool.step(jobs)
+        return idx, geds, wall, per
+
+    def close(self):
+        self.pool.close()
+
+
+def reference_available():
+    """oracle/_ref in place?  (placed by __graft_entry__.build() / oracle/build_ref.py in the build container; it travels
+    to the GPU box with the snapshot -- bench.py itself never reads /root/reference)"""
+    try:
+        from oracle import ref_runner
+        return ref_runner.available()
+    except Exception:
+        return False
+
+
 def run_reference(args):
-    """`--impl reference`: the reference's CPU implementation of the path (oracle port, all host threads)."""
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores (oracle/_ref when it
+    is in place, else the C port), on OUR arm's workload, metric and unit; every step a bounded sample of the batch."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    sample = args.cpu_sample or max(128, 8 * threads)
-    for _ in range(min(args.warmup, 1)):
-        cpu_baseline(args, max(threads, 8), threads)
-    vals, dts = [], []
-    for _ in range(max(args.steps, 1)):
-        v, dt, _, _ = cpu_baseline(args, sample, threads)
-        vals.append(v)
-        dts.append(dt)
-    value = sample * len(vals) / sum(dts)
+    cores = os.cpu_count() or 1
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * sum(dts) / len(dts), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args, 1), "sample": f"{sample} candidates per step"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample} candidates of the workload spread evenly over the batch, {threads} threads, "
-                                   "oracle/ged_oracle.c (C restatement of utils/ged_env.py IPFP/LSAPE path)"},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "gpu_launches": 0,
     }
+    port_value, port_dt, _, _ = cpu_port(args, args.cpu_sample or max(128, 8 * cores), cores)
+    port = {"value": port_value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{args.cpu_sample or max(128, 8 * cores)} candidates, {port_dt:.1f} s, oracle/ged_oracle.c on {cores} threads"}
+    if reference_available():
+        arm = ReferenceArm(args, cores)
+        try:
+            arm.warm(args.warmup)
+            walls, per = [], []
+            for k in range(max(args.steps, 1)):
+                _, _, wall, secs = arm.step(k)
+                walls.append(wall)
+                per += secs
+        finally:
+            arm.close()
+        value = cores * len(walls) / sum(walls)
+        sample = (f"{cores} candidates per step (one per worker process, spread evenly over the batch, a different comb every "
+                  f"step), {len(walls)} steps, {sum(walls):.1f} s; unmodified utils/ged_env.py GEDenv.step through oracle/ref_shim.py, "
+                  f"{cores} processes x 1 torch thread; mean {statistics.mean(per):.2f} s per candidate per core")
+        line.update({"value": value, "ms_per_step": 1e3 * sum(walls) / len(walls),
+                     "config": {"workload": workload_name(args, 1), "sample": f"{cores} candidates per step",
+                                "warmup_steps": f"{args.warmup} untimed steps of the same code at max_iter 3"},
+                     "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample,
+                                      "cpu_model": host_cpu_model(), "per_core_value_all_cores_busy": 1.0 / statistics.mean(per),
+                                      "port": port}})
+    else:
+        steps = max(args.steps, 1)
+        vals = [cpu_port(args, args.cpu_sample or max(128, 8 * cores), cores, phase=k) for k in range(steps)]
+        total = sum(v[1] for v in vals)
+        n = sum(len(v[2]) for v in vals)
+        line.update({"value": n / total, "ms_per_step": 1e3 * total / steps,
+                     "config": {"workload": workload_name(args, 1), "sample": f"{n // steps} candidates per step"},
+                     "cpu_baseline": dict(port, value=n / total, cpu_model=host_cpu_model(),
+                                          note="oracle/_ref (the reference's own files) is not in place on this box: C port timed")})
+    line["e2e"] = {"value": line["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     print(json.dumps(line), flush=True)
 
 
@@ -150,6 +228,58 @@ class ClockSampler:
         pw = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(rows), "power_w_max": max(pw) if pw else None}
+
+
+def issue_peaks():
+    """Issue roofs of THIS GPU, measured now by scripts/ubench/issue_peak (a few hundred ms); the copy stored with the
+    profiles is the fallback when the binary did not travel."""
+    exe = os.path.join(ROOT, "scripts", "ubench", "issue_peak")
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout.strip().splitlines()[-1]
+        peaks = json.loads(out)
+        if "fma_winst_per_s" in peaks:
+            return peaks, "measured in this run (scripts/ubench/issue_peak.cu)"
+    except (OSError, ValueError, IndexError, subprocess.SubprocessError):
+        pass
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "roofline_r02.json")))["issue_peaks"], "profiles/roofline_r02.json (stored measurement)"
+    except (OSError, KeyError, ValueError):
+        return None, "unavailable"
+
+
+def issue_roofline(args, world, kernel_ms, lap_steps_per_step):
+    """The binding roof of ged_solve_kernel is instruction issue (its busiest unit: the ALU pipe), not HBM or tensor cores
+    (DESIGN.md section 5).  achieved = warp instructions the step's solve launches EXECUTE (ncu smsp__inst_executed.sum of
+    this very workload, profiles/roofline_r02.json) / the step time measured here; peak = the FFMA issue rate measured on
+    this GPU (1 warp instruction per clock per SM sub-partition).  The ALU-pipe roof, the LAP scan-step rate and HBM are
+    reported beside it."""
+    peaks, src = issue_peaks()
+    prof = {}
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_r02.json")))
+    except (OSError, ValueError):
+        pass
+    sig = f"{args.config}|{args.pairs}|{args.edits}|{args.max_iter}"
+    w = prof.get("workloads", {}).get(sig)
+    roof = {"bound": "issue", "unit": "warp-instructions/s", "kernel": "ged_solve_kernel", "peak_source": src,
+            "lap_scan_steps_per_s": lap_steps_per_step / (kernel_ms * 1e-3) if lap_steps_per_step else None,
+            "lap_scan_steps_per_step": lap_steps_per_step}
+    if peaks:
+        roof["peak"] = peaks["fma_winst_per_s"]
+        roof["issue_peaks"] = peaks
+    if w and peaks:
+        inst = w["warp_instructions_per_step"]
+        roof.update({"achieved": inst / (kernel_ms * 1e-3), "frac": inst / (kernel_ms * 1e-3) / peaks["fma_winst_per_s"],
+                     "traffic": w.get("dram_bytes_per_step"), "warp_instructions_per_step": inst,
+                     "instructions_source": f"ncu smsp__inst_executed.sum over the step's launches, {w.get('source')}",
+                     "alu_pipe": {"achieved": w["alu_warp_instructions_per_step"] / (kernel_ms * 1e-3),
+                                  "peak": peaks["alu_winst_per_s"], "unit": "warp-instructions/s",
+                                  "frac": w["alu_warp_instructions_per_step"] / (kernel_ms * 1e-3) / peaks["alu_winst_per_s"]},
+                     "per_class": w.get("per_class")})
+    else:
+        roof.update({"achieved": None, "frac": None, "traffic": None,
+                     "note": f"no ncu instruction count stored for workload {sig!r} (profiles/roofline_r02.json)"})
+    return roof
 
 
 def algorithmic_bytes(pairs, base):
@@ -237,6 +367,13 @@ def main():
     ms_total = sum(ms for ms, _ in runs)
     res = runs[-1][1]
     launches = sum(r.launches for _, r in runs)
+    # LAP scan steps of one step (deterministic for a workload): one extra, untimed pass that asks the kernel for its counters
+    counted = solver.solve_batch(ps, base_idx=base_d, edit_u=eu_d, edit_v=ev_d, max_iter=args.max_iter, plan=plan, lap_steps=True)
+    lap_steps_local = torch.tensor([float(counted.trace["lap_steps"].sum().item())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(lap_steps_local)
+    lap_steps_per_step = float(lap_steps_local[0])
+    assert torch.equal(counted.ged, res.ged)
     status_bad = int((res.status != 0).sum().item())
     mean_iters = float(res.iters.float().mean().item())
     mean_ged = float(res.ged.mean().item())
@@ -275,12 +412,11 @@ def main():
         hbm_peak, which = (peaks["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
         alg = algorithmic_bytes(pairs, base)
         kernel_ms = ms_total / args.steps             # the solve launches ARE the step (one kernel, one launch per size class)
-        achieved = alg / (kernel_ms * 1e-3) / 1e9
-        extra = {}
-        try:
-            extra = json.load(open(os.path.join(ROOT, "profiles", "roofline_r01.json")))
-        except OSError:
-            pass
+        hbm_achieved = alg / (kernel_ms * 1e-3) / 1e9
+        roof = issue_roofline(args, world, kernel_ms, lap_steps_per_step)
+        roof["hbm"] = {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                       "peak_source": which, "algorithmic_bytes_per_step": alg,
+                       "note": "not the binding roof: ~1e3 executed instructions per compulsory byte"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -292,25 +428,39 @@ def main():
                     "d2h_bytes_per_step": host_batch.d2h_bytes, "ms_per_step": e2e_total / args.steps},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": extra.get("dram_bytes_per_launch"), "peak_source": which,
-                         "algorithmic_bytes_per_step": alg, "kernel": "ged_solve_kernel",
-                         "note": "compute per byte is ~1e3 instructions: the kernel is bound by instruction issue of the "
-                                 "sequential LAP scan -- its busiest unit is the ALU pipe -- not by HBM (DESIGN.md); the ncu "
-                                 "figures of the dominant launch are in `issue_active_pct` and `binding_unit`",
-                         "issue_active_pct": extra.get("issue_active_pct"),
-                         "binding_unit": {"unit": "SM ALU pipe (sm__inst_executed_pipe_alu)", "pct_of_peak": extra.get("alu_pipe_pct"),
-                                          "fp64_pipe_pct": extra.get("fp64_pipe_active_pct"), "fma_pipe_pct": extra.get("fma_pipe_pct")}},
+            "roofline": roof,
         }
         if not args.no_cpu_baseline and world == 1:      # reported at N=1 only
-            threads = os.cpu_count() or 1
-            sample = args.cpu_sample or max(128, 8 * threads)
-            v, dt, idx, geds = cpu_baseline(args, sample, threads)
-            same = bool(np.array_equal(np.asarray(geds, np.float32), res.ged.cpu().numpy()[idx]))
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{sample} candidates of the same workload spread evenly over rank 0's batch, "
-                                              f"{dt:.1f} s, oracle/ged_oracle.c on {threads} threads",
-                                    "gpu_results_identical_on_sample": same}
+            cores = os.cpu_count() or 1
+            sample = args.cpu_sample or max(128, 8 * cores)
+            v, dt, idx, geds = cpu_port(args, sample, cores)
+            ged_gpu = res.ged.cpu().numpy()
+            same = bool(np.array_equal(np.asarray(geds, np.float32), ged_gpu[idx]))
+            port = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"{sample} candidates of the same workload spread evenly over rank 0's batch, "
+                              f"{dt:.1f} s, oracle/ged_oracle.c on {cores} threads",
+                    "gpu_results_identical_on_sample": same}
+            if reference_available():
+                arm = ReferenceArm(args, cores)
+                try:
+                    arm.warm(1)
+                    ridx, rgeds, wall, per = arm.step(0)
+                finally:
+                    arm.close()
+                ours = ged_gpu[ridx]
+                line["cpu_baseline"] = {
+                    "value": cores / wall, "unit": UNIT, "cores": cores, "kind": "reference", "cpu_model": host_cpu_model(),
+                    "sample": f"{cores} candidates of the same workload (one per worker process, spread evenly over rank 0's batch), "
+                              f"{wall:.1f} s; unmodified utils/ged_env.py GEDenv.step through oracle/ref_shim.py, {cores} processes x 1 "
+                              f"torch thread; {statistics.mean(per):.2f} s per candidate per core",
+                    "per_core_value_all_cores_busy": 1.0 / statistics.mean(per),
+                    "objective_on_sample": {"reference_mean": float(np.mean(rgeds)), "gpu_mean": float(np.mean(ours)),
+                                            "identical": int(np.sum(np.asarray(rgeds, np.float32) == ours)), "of": len(ridx),
+                                            "note": "the reference's fp32 trajectory is chaotic under summation order "
+                                                    "(it disagrees with itself across MKL thread counts): DESIGN.md section 4"},
+                    "port": port}
+            else:
+                line["cpu_baseline"] = dict(port, cpu_model=host_cpu_model())
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -430,10 +430,27 @@ typedef struct {
 
 /* ipfp_ged (utils/ged_env.py:256-289) on the pair (adj1 with the optional edit (eu,ev) applied, adj2), scored on
  * the UNEDITED pair as GEDenv.step does (utils/ged_env.py:122,158).  solver: 0 = ipfp, 1 = hungarian only. */
+int ged_oracle_solve_from(int n1, int n2, const uint8_t *adj1, const uint8_t *adj2, const float *Cn,
+                          int eu, int ev, int max_iter, int solver, const float *x_init,
+                          int32_t *out_rowmatch, int32_t *out_colmatch, float *out_ged, float *out_ged_edited,
+                          int32_t *out_iters, ged_trace *tr);
+
 int ged_oracle_solve(int n1, int n2, const uint8_t *adj1, const uint8_t *adj2, const float *Cn,
                      int eu, int ev, int max_iter, int solver,
                      int32_t *out_rowmatch, int32_t *out_colmatch, float *out_ged, float *out_ged_edited,
                      int32_t *out_iters, ged_trace *tr)
+{
+    return ged_oracle_solve_from(n1, n2, adj1, adj2, Cn, eu, ev, max_iter, solver, NULL, out_rowmatch, out_colmatch, out_ged,
+                                 out_ged_edited, out_iters, tr);
+}
+
+/* The same with an optional start iterate x_init (R x C fp32; NULL = the Hungarian start): teacher forcing of single
+ * IPFP iterations from the reference's own iterates (tests/test_oracle_trajectory.py), mirroring ged_solve_desc.x_init of the
+ * C-ABI.  With x_init the "best" solution before the first iteration is "everything deleted / inserted". */
+int ged_oracle_solve_from(int n1, int n2, const uint8_t *adj1, const uint8_t *adj2, const float *Cn,
+                          int eu, int ev, int max_iter, int solver, const float *x_init,
+                          int32_t *out_rowmatch, int32_t *out_colmatch, float *out_ged, float *out_ged_edited,
+                          int32_t *out_iters, ged_trace *tr)
 {
     const int R = n1 + 1, C = n2 + 1, RC = R * C;
     int st = GED_OK;
@@ -452,19 +469,25 @@ int ged_oracle_solve(int n1, int n2, const uint8_t *adj1, const uint8_t *adj2, c
     int64_t total_steps = 0, steps = 0;
     int iters = 0;
 
-    /* hungarian_ged: v0 = LSAPE(node_cost_mat) */
-    ged_oracle_init_cost_closed_form(n1, n2, a1, a2, cost);
-    if (tr && tr->init_cost) memcpy(tr->init_cost, cost, sizeof(float) * RC);
-    st = ged_oracle_lsape(n1, n2, cost, rm, cm, NULL, &steps);
-    total_steps += steps;
-    if (st != GED_OK) goto done;
-    if (tr && tr->init_rowmatch) memcpy(tr->init_rowmatch, rm, sizeof(int32_t) * n1);
-    if (tr && tr->init_colmatch) memcpy(tr->init_colmatch, cm, sizeof(int32_t) * n2);
-    memcpy(brm, rm, sizeof(int32_t) * n1);
-    memcpy(bcm, cm, sizeof(int32_t) * n2);
+    if (x_init) {
+        for (int i = 0; i < n1; ++i) brm[i] = n2;
+        for (int a = 0; a < n2; ++a) bcm[a] = n1;
+    } else {
+        /* hungarian_ged: v0 = LSAPE(node_cost_mat) */
+        ged_oracle_init_cost_closed_form(n1, n2, a1, a2, cost);
+        if (tr && tr->init_cost) memcpy(tr->init_cost, cost, sizeof(float) * RC);
+        st = ged_oracle_lsape(n1, n2, cost, rm, cm, NULL, &steps);
+        total_steps += steps;
+        if (st != GED_OK) goto done;
+        if (tr && tr->init_rowmatch) memcpy(tr->init_rowmatch, rm, sizeof(int32_t) * n1);
+        if (tr && tr->init_colmatch) memcpy(tr->init_colmatch, cm, sizeof(int32_t) * n2);
+        memcpy(brm, rm, sizeof(int32_t) * n1);
+        memcpy(bcm, cm, sizeof(int32_t) * n2);
+    }
 
     if (solver == 0) {
-        dense_from_match(n1, n2, rm, cm, X);
+        if (x_init) memcpy(X, x_init, sizeof(float) * RC);
+        else dense_from_match(n1, n2, rm, cm, X);
         double best_ub = INFINITY;
         for (int it = 0; it < max_iter; ++it) {
             iters = it + 1;
@@ -510,4 +533,4 @@ done:
     return st;
 }
 
-const char *ged_oracle_version(void) { return "ged_oracle 2 (canonical order v2)"; }
+const char *ged_oracle_version(void) { return "ged_oracle 3 (canonical order v2; x_init)"; }

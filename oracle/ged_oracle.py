@@ -136,8 +136,9 @@ def score(adj1, adj2, Cn, rowmatch, colmatch):
     return lib().ged_oracle_score(n1, n2, _p(adj1, c_u8p), _p(adj2, c_u8p), _p(Cn, c_f32p), _p(rm, c_i32p), _p(cm, c_i32p))
 
 
-def solve(adj1, adj2, Cn, edit=None, max_iter=100, solver="ipfp", trace=False):
-    """Canonical-order ipfp_ged / hungarian_ged + scoring on the unedited pair.
+def solve(adj1, adj2, Cn, edit=None, max_iter=100, solver="ipfp", trace=False, x_init=None):
+    """Canonical-order ipfp_ged / hungarian_ged + scoring on the unedited pair.  ``x_init`` ((n1+1) x (n2+1) fp32) replaces
+    the Hungarian start (teacher forcing, like ``ged_solve_desc.x_init``).
 
     Returns dict(rowmatch, colmatch, ged, ged_edited, iters[, trace...]).
     """
@@ -162,8 +163,12 @@ def solve(adj1, adj2, Cn, edit=None, max_iter=100, solver="ipfp", trace=False):
                     init_rowmatch=np.zeros(n1, np.int32), init_colmatch=np.zeros(n2, np.int32),
                     init_cost=np.zeros((R, C), np.float32), lap_steps=np.zeros(1, np.int64))
         tr = _Trace(*[_p(keep[name], typ) for name, typ in _Trace._fields_])
-    st = lib().ged_oracle_solve(n1, n2, _p(adj1, c_u8p), _p(adj2, c_u8p), _p(Cn, c_f32p), eu, ev, int(max_iter),
-                                0 if solver == "ipfp" else 1, _p(rm, c_i32p), _p(cm, c_i32p),
+    if x_init is not None:
+        x_init = np.ascontiguousarray(x_init, np.float32)
+        assert x_init.shape == (R, C)
+    st = lib().ged_oracle_solve_from(n1, n2, _p(adj1, c_u8p), _p(adj2, c_u8p), _p(Cn, c_f32p), eu, ev, int(max_iter),
+                                0 if solver == "ipfp" else 1, _p(x_init, c_f32p) if x_init is not None else None,
+                                _p(rm, c_i32p), _p(cm, c_i32p),
                                 ctypes.byref(ged), ctypes.byref(ged_e), ctypes.byref(iters),
                                 ctypes.byref(tr) if tr is not None else None)
     if st:

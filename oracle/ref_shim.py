@@ -21,6 +21,9 @@ import types
 import torch
 
 REFERENCE_ROOT = os.environ.get("PPO_BIHYB_REFERENCE", "/root/reference")
+if not os.path.isfile(os.path.join(REFERENCE_ROOT, "utils", "ged_env.py")):
+    # the GPU box has no /root/reference: oracle/_ref (oracle/build_ref.py; git-ignored, travels with the snapshot)
+    REFERENCE_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 
 
 def reference_available() -> bool:

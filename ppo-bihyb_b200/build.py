@@ -30,16 +30,20 @@ def needs_build() -> bool:
     return any(os.path.getmtime(f) > t for f in (SRC, HDR, __file__))
 
 
-def build(force: bool = False, verbose: bool = False, extra=()) -> str:
-    if not (force or needs_build()):
+def build(force: bool = False, verbose: bool = False, extra=(), out: str = None) -> str:
+    """``out``: build a VARIANT library next to the product one (``libged_b200.<out>.so``, objects in ``build/<out>/``) for
+    in-process A/B runs through ``GED_B200_LIBRARY``; the product library is only ever built without it."""
+    if out is None and not (force or needs_build()):
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    os.makedirs(OBJ_DIR, exist_ok=True)
+    obj_dir = OBJ_DIR if out is None else os.path.join(OBJ_DIR, out)
+    target = OUT if out is None else os.path.join(HERE, f"libged_b200.{out}.so")
+    os.makedirs(obj_dir, exist_ok=True)
     units = [("main", [])] + [(f"s{k}", [f"-DGED_TU_S={k}"]) for k in SLOT_COUNTS]
 
     def compile_unit(unit):
         name, defs = unit
-        obj = os.path.join(OBJ_DIR, f"ged_{name}.o")
+        obj = os.path.join(obj_dir, f"ged_{name}.o")
         cmd = [nvcc] + NVCC_FLAGS + list(extra) + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, SRC]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or res.returncode:
@@ -50,10 +54,13 @@ def build(force: bool = False, verbose: bool = False, extra=()) -> str:
 
     with ThreadPoolExecutor(max_workers=min(len(units), os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_unit, units))
-    subprocess.check_call([nvcc, "-shared", "-o", OUT] + objs)
-    return OUT
+    subprocess.check_call([nvcc, "-shared", "-o", target] + objs)
+    return target
 
 
 if __name__ == "__main__":
     extra = [a for a in sys.argv[1:] if a.startswith("-D")]
-    print(build(force="--force" in sys.argv or bool(extra), verbose="-v" in sys.argv, extra=extra))
+    variant = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")), None)
+    if extra and variant is None:
+        raise SystemExit("-D flags build a variant: name it with --out=<name> (the product library is built without flags)")
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, extra=extra, out=variant))

@@ -345,6 +345,32 @@ __device__ __forceinline__ double double_from_ord(unsigned ohi, unsigned olo)
 // ---- per-slot building blocks of the LAP scan step, written as PTX so that each is exactly the intended handful of
 // SASS instructions (LOP3 -> predicate, DSETP with the predicate folded in, selects) without moves or branches -----------
 
+// Scan-step shortcut (GED_LAP_SHORTCUT, default on).  Every shortest-path cost of a column still in `remaining` is >= minVal
+// (minVal was their minimum when it was set, and only a relaxation changes one afterwards), so after a row's relaxations the
+// new minimum is minVal itself unless (a) a value written by this row is BELOW minVal (possible through rounding only, and at
+// the first row of a search, where minVal = 0) or (b) no remaining column attains minVal any more.  minVal stays the same in
+// 89 % of the scan steps of an AIDS-50+ solve, so a step first bids for the tie-break key at the OLD minVal -- a lane that saw
+// (a) bids key 0 -- and only recomputes the 64-bit minimum (two more warp reductions, the order-preserving split, the
+// per-slot minimum chain) when the winning bid is 0 (a) or ~0 (b).
+#ifndef GED_LAP_SHORTCUT
+#define GED_LAP_SHORTCUT 1
+#endif
+
+// if (live & MASK) && r < spc:  spc = r, pth = i, and below = 1 if also r < minVal
+template <unsigned MASK>
+__device__ __forceinline__ void lap_relax_below(double &spc, int &pth, int &below, double r, int i, unsigned live, double minVal)
+{
+    asm("{\n\t.reg .pred q, p, p2;\n\t.reg .b32 t;\n\t"
+        "and.b32 t, %5, %6;\n\t"
+        "setp.ne.u32 q, t, 0;\n\t"
+        "setp.lt.and.f64 p, %3, %0, q;\n\t"
+        "selp.f64 %0, %3, %0, p;\n\t"
+        "selp.b32 %1, %4, %1, p;\n\t"
+        "setp.lt.and.f64 p2, %3, %7, p;\n\t"
+        "@p2 mov.b32 %2, 1;\n\t}"
+        : "+d"(spc), "+r"(pth), "+r"(below) : "d"(r), "r"(i), "r"(live), "n"(MASK), "d"(minVal));
+}
+
 // if (live & MASK) && r < spc:  spc = r, pth = i (and, when TRACK, improved = 1)
 template <unsigned MASK, bool TRACK = true>
 __device__ __forceinline__ void lap_relax(double &spc, int &pth, int &improved, double r, int i, unsigned live)
@@ -424,6 +450,34 @@ struct LapSlots {
                 }
             }
             LapSlots<S, I + 1>::template relax_one<LO, HI, TRACK>(spc, pth, improved, v, base, i, live_lane, sel);
+        }
+    }
+    // the same three with the `below` flag of the scan-step shortcut (see lap_relax_below)
+    template <int LO, int HI>
+    static __device__ __forceinline__ void relax_base_below(double (&spc)[2 * S], int (&pth)[2 * S], int &below,
+                                                            const double (&v)[2 * S], double base, int i, unsigned live, double minVal)
+    {
+        if constexpr (I < 2 * S) {
+            if constexpr (I >= LO && I < HI)
+                lap_relax_below<(1u << I)>(spc[I], pth[I], below, __dsub_rn(base, v[I]), i, live, minVal);
+            LapSlots<S, I + 1>::template relax_base_below<LO, HI>(spc, pth, below, v, base, i, live, minVal);
+        }
+    }
+    template <int LO, int HI>
+    static __device__ __forceinline__ void relax_one_below(double (&spc)[2 * S], int (&pth)[2 * S], int &below,
+                                                           const double (&v)[2 * S], double base, int i, unsigned live_lane, int sel,
+                                                           double minVal)
+    {
+        relax_base_below<LO, HI>(spc, pth, below, v, base, i, live_lane & ((1u << LO) << sel), minVal);
+    }
+    static __device__ __forceinline__ void relax_row_below(double (&spc)[2 * S], int (&pth)[2 * S], int &below,
+                                                           const double (&v)[2 * S], const float (&cs)[S], double minVal, double ui,
+                                                           int i, unsigned live)
+    {
+        if constexpr (I < S) {
+            const double r = __dsub_rn(__dsub_rn(__dadd_rn(minVal, (double)cs[I]), ui), v[I]);
+            lap_relax_below<(1u << I)>(spc[I], pth[I], below, r, i, live, minVal);
+            LapSlots<S, I + 1>::relax_row_below(spc, pth, below, v, cs, minVal, ui, i, live);
         }
     }
     // real slots [0, S): relax with SciPy's r = ((minVal + c) - u[i]) - v[j]
@@ -522,6 +576,32 @@ __device__ int lsape_warp(const Store &store, bool invalid, int n1, int n2, cons
             int improved = 0;
             unsigned lk = 0xffffffffu;
             bool need_min = true;
+#if GED_LAP_SHORTCUT
+            if (real) {                      // real row: n2 substitution entries + its own deletion entry
+                if (Store::kPrefetch) store.row_wait(i, cs);       // pairs with the row_issue of the previous step / prologue
+                else store.row(i, cs);
+                LapSlots<S>::relax_row_below(spc, pth, improved, v, cs, minVal, ui, i, live);
+                const double rd = __dsub_rn(__dadd_rn(minVal, (double)cx), ui);
+                LapSlots<S>::template relax_one_below<S, 2 * S>(spc, pth, improved, v, rd, i, (lane == (i & 31)) ? live : 0u, i >> 5, minVal);
+            } else {                         // insertion row of column a0: its own entry + the zero block
+                const int a0 = i - n1;
+                const double ra = __dsub_rn(__dadd_rn(minVal, (double)cx), ui);
+                LapSlots<S>::template relax_one_below<0, S>(spc, pth, improved, v, ra, i, (lane == (a0 & 31)) ? live : 0u, a0 >> 5, minVal);
+                // zero block: r = rz - v[j].  Rounding is monotone in rz, and after a scan with value rz0 every remaining
+                // deletion column has spc <= fl(rz0 - v[j]); a later insertion row with rz >= rz0 cannot lower any of them.
+                const double rz = __dsub_rn(__dadd_rn(minVal, 0.0), ui);
+                if (rz < rzmin) {
+                    rzmin = rz;
+                    LapSlots<S>::template relax_base_below<S, 2 * S>(spc, pth, improved, v, rz, i, live, minVal);
+                }
+            }
+            // Tie-break among the columns that attain the OLD minVal (see GED_LAP_SHORTCUT above): `improved` here means
+            // "this lane wrote a value below minVal" and bids key 0, below every real key.
+            LapSlots<S>::min_key(lk, spc, minVal, live, posk, kx);
+            lk = improved ? 0u : lk;
+            mk = __reduce_min_sync(kFull, lk);
+            need_min = (mk - 1u >= 0xfffffffeu);
+#else
             if (real) {                      // real row: n2 substitution entries + its own deletion entry
                 if (Store::kPrefetch) store.row_wait(i, cs);       // pairs with the row_issue of the previous step / prologue
                 else store.row(i, cs);
@@ -548,6 +628,7 @@ __device__ int lsape_warp(const Store &store, bool invalid, int n1, int n2, cons
                 mk = __reduce_min_sync(kFull, lk);
                 need_min = (mk - 1u >= 0xfffffffeu);
             }
+#endif
             if (need_min) {
                 double lmA = INFINITY, lmB = INFINITY;          // two independent chains
                 LapSlots<S>::min_value2(lmA, lmB, spc, live);

@@ -101,13 +101,14 @@ def solve_batch(pairs: PairSet, base_idx=None, edit_u=None, edit_v=None, solver:
                 x_init: Optional[torch.Tensor] = None, dense_x: bool = False, trace: bool = False,
                 check: bool = False, score_adj1: Optional[torch.Tensor] = None,
                 score_adj1_off: Optional[torch.Tensor] = None, score_idx=None, size_classes: bool = True,
-                plan=None, score_adj1_ld: int = 0) -> SolveResult:
+                plan=None, score_adj1_ld: int = 0, lap_steps: bool = False) -> SolveResult:
     """All candidate solves of one batch (``ged_solve_batch``): one launch per size class, concurrently on side
     streams, results in candidate order.
 
     Candidate b = base pair ``base_idx[b]`` with edge ``(edit_u[b], edit_v[b])`` of graph 1 toggled
     (reference ``GEDenv.step``, ``utils/ged_env.py:110-124``).  ``plan`` = a cached ``(order_device, classes)`` from
-    :func:`make_plan` avoids re-planning when the same candidate list is solved repeatedly."""
+    :func:`make_plan` avoids re-planning when the same candidate list is solved repeatedly.  ``lap_steps`` also returns the
+    number of LAP scan steps every solve executed (``result.trace["lap_steps"]``; the work figure of the roofline)."""
     lib = _lib.require_cuda()
     if solver not in SOLVERS:
         raise NotImplementedError(f"{solver} is not implemented.")      # reference ged_env.py:156
@@ -155,6 +156,8 @@ def solve_batch(pairs: PairSet, base_idx=None, edit_u=None, edit_v=None, solver:
                   rowmatch=torch.zeros(B, T, m1, **i32), colmatch=torch.zeros(B, T, m2, **i32),
                   init_cost=torch.zeros(B, ms, **f32), init_rowmatch=torch.zeros(B, m1, **i32),
                   init_colmatch=torch.zeros(B, m2, **i32), lap_steps=torch.zeros(B, device=dev, dtype=torch.int64))
+    if lap_steps and "lap_steps" not in tr:
+        tr["lap_steps"] = torch.zeros(B, device=dev, dtype=torch.int64)
     p = _lib.ptr
     desc = _lib.GedSolveDesc(pairs.c_struct(), B, p(base_idx, _lib.c_i32p), p(edit_u, _lib.c_i32p), p(edit_v, _lib.c_i32p),
                              p(score_adj1, _lib.c_u8p), p(score_adj1_off, _lib.c_i64p), p(score_idx, _lib.c_i32p),

@@ -1,0 +1,98 @@
+"""In-box A/B of kernel builds (development aid).  Each library (``name=path`` arguments; ``prod`` = the product library) runs
+the same workloads in its own process, alternating, best of ``--reps``; a checksum of the results shows that the builds
+agree bit for bit.   python scripts/ab_libs.py prod base=ppo-bihyb_b200/libged_b200.base.so [--work n=60:128x64,...]"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEFAULT_WORK = "n=60:128x64,n=80:64x64,n=100:64x32,aids-20-30:64x64,aids-30-50:64x64,aids-50+:128x64,aids-50+:10x27,aids-50+:64x1"
+
+
+def worker(work, reps):
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import torch
+    from ppo_bihyb_b200 import solver, synthetic
+    from ppo_bihyb_b200.graphs import PairSet
+    dev = torch.device("cuda:0")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = {}
+    for item in work.split(","):
+        config, shape = item.split(":")
+        P, E = (int(x) for x in shape.split("x"))
+        pairs = synthetic.make_pairs(config, P, seed_offset=3)
+        edits = synthetic.make_edits(pairs, E, seed_offset=3)
+        ps = PairSet.from_host(pairs, dev)
+        plan = solver.make_plan(ps, edits[0])
+        best = None
+        for rep in range(reps + 1):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res = solver.solve_batch(ps, base_idx=edits[0], edit_u=edits[1], edit_v=edits[2], plan=plan)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            if rep > 0:
+                best = ms if best is None else min(best, ms)
+        assert int((res.status != 0).sum()) == 0
+        chk = (float(res.ged.double().sum()), int(res.iters.sum()), int(res.rowmatch.long().sum()), int(res.colmatch.long().sum()))
+        out[item] = dict(ms=best, B=len(edits[0]), chk=chk)
+    print("RESULT " + json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("libs", nargs="*")
+    ap.add_argument("--work", default=DEFAULT_WORK)
+    ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--rounds", type=int, default=2)
+    ap.add_argument("--worker", action="store_true")
+    args = ap.parse_args()
+    if args.worker:
+        return worker(args.work, args.reps)
+    libs = []
+    for spec in args.libs or ["prod"]:
+        name, _, path = spec.partition("=")
+        libs.append((name, os.path.abspath(path) if path else None))
+    best = {name: {} for name, _ in libs}
+    chk = {name: {} for name, _ in libs}
+    for rnd in range(args.rounds):
+        for name, path in libs:
+            env = dict(os.environ)
+            env.pop("GED_B200_LIBRARY", None)
+            if path:
+                env["GED_B200_LIBRARY"] = path
+            res = subprocess.run([sys.executable, os.path.abspath(__file__), "--worker", "--work", args.work, "--reps", str(args.reps)],
+                                 env=env, capture_output=True, text=True)
+            line = next((l for l in res.stdout.splitlines() if l.startswith("RESULT ")), None)
+            if line is None:
+                print(f"{name}: FAILED\n{res.stdout[-2000:]}\n{res.stderr[-4000:]}")
+                continue
+            for item, r in json.loads(line[7:]).items():
+                best[name][item] = min(best[name].get(item, 1e30), r["ms"])
+                chk[name][item] = (r["chk"], r["B"])
+    items = args.work.split(",")
+    ref = libs[0][0]
+    print("| workload | " + " | ".join(f"{n} ms (solves/s)" for n, _ in libs) + " | vs " + ref + " | same bits |")
+    print("|---|" + "---|" * (len(libs) + 2))
+    for item in items:
+        cells, ratio, same = [], [], []
+        for n, _ in libs:
+            if item not in best[n]:
+                cells.append("failed")
+                continue
+            B = chk[n][item][1]
+            cells.append(f"{best[n][item]:.1f} ({B / best[n][item] * 1e3:,.0f})")
+            if n != ref and item in best[ref]:
+                ratio.append(f"{best[ref][item] / best[n][item]:.3f}x")
+                same.append("yes" if chk[n][item][0] == chk[ref][item][0] else "NO")
+        print(f"| {item} | " + " | ".join(cells) + " | " + ", ".join(ratio) + " | " + ", ".join(same) + " |")
+
+
+if __name__ == "__main__":
+    main()

@@ -79,3 +79,36 @@ def test_invalid_and_infeasible_inputs():
         go.lsap(np.array([[np.inf, np.inf], [1.0, 0.0]]))
     with pytest.raises(ValueError):
         opt.linear_sum_assignment(np.array([[np.inf, np.inf], [1.0, 0.0]]))
+
+
+def test_lsape_equals_scipy_at_path_sizes():
+    """The sizes the path really runs at (round-1 review: SciPy was only consulted up to n = 24): 60 matrices with n1, n2 in
+    [50, 100], 6 with n in [150, 200] -- integer ties, k/3 fractions, uniform -- and real IPFP iteration costs of an
+    AIDS-50+ solve: the oracle's implicit expansion == SciPy on the expanded (n1+n2)^2 matrix."""
+    from ppo_bihyb_b200 import synthetic
+    from ppo_bihyb_b200.graphs import label_node_cost
+    rng = np.random.default_rng(31)
+    mats = []
+    for count, lo, hi in ((60, 50, 100), (6, 150, 200)):
+        for t in range(count):
+            n1, n2 = int(rng.integers(lo, hi + 1)), int(rng.integers(lo, hi + 1))
+            c = (rng.integers(0, 3, (n1 + 1, n2 + 1)).astype(np.float32) if t % 3 == 0 else
+                 (rng.integers(0, 7, (n1 + 1, n2 + 1)) / 3.0).astype(np.float32) if t % 3 == 1 else
+                 rng.random((n1 + 1, n2 + 1)).astype(np.float32))
+            mats.append(c)
+    g1, g2 = synthetic.make_pairs("aids-50+", 1, seed_offset=19)[0]
+    o = go.solve(g1.adj, g2.adj, label_node_cost(g1.labels, g2.labels), trace=True)
+    mats += [o["cost"][i] for i in range(0, o["iters"], 5)]
+    for t, C in enumerate(mats):
+        n1, n2 = C.shape[0] - 1, C.shape[1] - 1
+        big = np.full((n1 + n2, n1 + n2), np.inf)
+        big[:n1, :n2] = C[:n1, :n2]
+        big[np.arange(n1), n2 + np.arange(n1)] = C[:n1, n2]
+        big[n1 + np.arange(n2), np.arange(n2)] = C[n1, :n2]
+        big[n1:, n2:] = 0.0
+        row, col = opt.linear_sum_assignment(big)
+        r4c = np.empty(n1 + n2, np.int64)
+        r4c[col] = row
+        rm, cm, _, _ = go.lsape(C)
+        assert np.array_equal(rm, np.where(col[:n1] < n2, col[:n1], n2)), t
+        assert np.array_equal(cm, np.where(r4c[:n2] < n1, r4c[:n2], n1)), t
