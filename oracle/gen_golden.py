@@ -15,6 +15,7 @@ Fixtures
   kv.npz           torch.mm(k, v) (ged_env.py:269) for random fractional v on the reference's dense K
   solve.npz        ipfp_ged / hungarian_ged + comp_ged end to end (ged_env.py:140-158): x, ged
   step.npz         GEDenv.step (ged_env.py:110-124): (pair, act) -> reward, new_solution, new edge_index
+  other_metrics.npz  construct_k with the non-AIDS node_metric tables (ged_env.py:235-242) + hungarian / ipfp objectives
 """
 import os
 import sys
@@ -227,7 +228,43 @@ def gen_step(ref, env):
                         **pairs_blob(pairs))
 
 
+def gen_other_metrics(ref):
+    """construct_k / node_metric for the NON-AIDS tables (ged_env.py:235-242: CMU / Willow [0, VERY_LARGE_INT, 0], any other
+    dataset [0, 1, 0]; the whole feature row is compared, ori_feature_dim = 0) and hungarian_ged / ipfp_ged on that K."""
+    rng = np.random.default_rng(606)
+    out = {}
+    for tag, dataset in (("willow", "Willow"), ("other", "SomeOtherDataset")):
+        env = ref_shim.make_reference_env("ipfp", dataset, 0)
+        pairs = small_pairs(4, 5, 11, 707 + len(tag))
+        ks, xs, geds, gedh, feats1, feats2 = [], [], [], [], [], []
+        for g1, g2 in pairs:
+            f1 = np.eye(3, dtype=np.float32)[rng.integers(0, 3, g1.n)]
+            f2 = np.eye(3, dtype=np.float32)[rng.integers(0, 3, g2.n)]
+            d1 = ref_shim.make_data(torch.from_numpy(f1), torch.from_numpy(g1.edge_index()))
+            d2 = ref_shim.make_data(torch.from_numpy(f2), torch.from_numpy(g2.edge_index()))
+            k = env.construct_k(d1, d2).squeeze(0)
+            xh = ref.hungarian_ged(k, g1.n, g2.n)
+            ks.append(k.numpy())
+            xs.append(xh.numpy())
+            gedh.append(float(ref.GEDenv.comp_ged(xh, k)))
+            geds.append(float(ref.GEDenv.comp_ged(ref.ipfp_ged(k, g1.n, g2.n), k)))
+            feats1.append(f1)
+            feats2.append(f2)
+        out[tag + "_k"], out[tag + "_k_off"] = pack_ragged(ks, np.float32)
+        out[tag + "_x_hungarian"], out[tag + "_off"] = pack_ragged(xs, np.float32)
+        out[tag + "_feat1"], out[tag + "_f1_off"] = pack_ragged(feats1, np.float32)
+        out[tag + "_feat2"], out[tag + "_f2_off"] = pack_ragged(feats2, np.float32)
+        out[tag + "_ged_hungarian"] = np.asarray(gedh, np.float32)
+        out[tag + "_ged_ipfp"] = np.asarray(geds, np.float32)
+        out.update(pairs_blob(pairs, prefix=tag + "_"))
+    np.savez_compressed(os.path.join(OUT, "other_metrics.npz"), **out)
+
+
 def main():
+    if "--other-metrics" in sys.argv:       # add this one fixture without regenerating the rest
+        torch.set_num_threads(1)
+        gen_other_metrics(ref_shim.load_reference())
+        return
     if not ref_shim.reference_available():
         raise SystemExit("reference tree not found; golden vectors can only be generated in the build container")
     torch.set_num_threads(1)
@@ -237,7 +274,7 @@ def main():
     import scipy
     t = time.time()
     for fn, args in ((gen_lsape, (ref,)), (gen_construct_k, (env,)), (gen_init, (ref, env)),
-                     (gen_iter0_and_kv, (ref, env)), (gen_solve, (ref, env)), (gen_step, (ref, env))):
+                     (gen_iter0_and_kv, (ref, env)), (gen_solve, (ref, env)), (gen_step, (ref, env)), (gen_other_metrics, (ref,))):
         print(fn.__name__, flush=True)
         fn(*args)
     with open(os.path.join(OUT, "PROVENANCE.txt"), "w") as f:

@@ -115,30 +115,64 @@ def hungarian_lap(node_cost_mat: torch.Tensor, n1, n2):
 
 
 def hungarian(s: torch.Tensor, n1=None, n2=None, mask=None, nproc=1):
-    """Maximum-weight square assignment, SciPy order (reference ``hungarian`` :354-398 -> ``hung_kernel`` :401-421).
+    """Maximum-weight assignment, SciPy order (reference ``hungarian`` :354-398 -> ``hung_kernel`` :401-421): 2-D or batched
+    3-D scores; ``n1`` / ``n2`` (1-D tensors, one entry per batch item) crop item b to ``s[b, :n1[b], :n2[b]]`` before the solve
+    (:405-407), ``mask`` (a boolean matrix per item selecting a row set x column set) solves on that sub-block (:409-418);
+    the result is a 0/1 matrix of the input's shape with the assigned pairs set.  ``nproc`` is accepted and ignored: every
+    item is one warp of a single launch.
 
-    Only what the GED path uses is supported: square 2-D / batched 3-D input, no mask, no per-sample cropping.  The
-    square LAP is embedded in the LSAPE kernel with +inf insertion/deletion costs, which leaves SciPy's scan order on
-    the real block unchanged."""
+    A rectangular LAP with nr <= nc is embedded in the LSAPE kernel with +inf deletion and zero insertion costs: the real
+    rows' searches see SciPy's ``remaining`` order on the real columns unchanged (the never-reachable deletion columns sit in
+    front of them and are never removed), and the insertion rows that follow take their free zero-cost deletion columns
+    without re-routing anything.  nr > nc is solved transposed, as SciPy does."""
     if len(s.shape) == 2:
         s3, matrix_input = s.unsqueeze(0), True
     elif len(s.shape) == 3:
         s3, matrix_input = s, False
     else:
         raise ValueError('input data shape not understood.')
-    if mask is not None or n1 is not None or n2 is not None or s3.shape[1] != s3.shape[2]:
-        raise NotImplementedError('hungarian(): only square, unmasked problems are on the B200 path')
-    B, n, _ = s3.shape
+    B, H, W = s3.shape
     _lib.require_cuda()
     dev = _default_device(s3)
-    cost = torch.full((B, n + 1, n + 1), float('inf'), device=dev, dtype=torch.float32)
-    cost[:, :n, :n] = -s3.detach().to(device=dev, dtype=torch.float32)
-    cost[:, n, n] = 0
-    rm, _, _, _ = solver.lsape_batch(cost.reshape(B, -1), n, n, check=True)
-    perm = torch.zeros(B, n, n, device=dev, dtype=torch.float32)
-    if bool((rm >= n).any().item()):
-        raise ValueError('cost matrix is infeasible')
-    perm.scatter_(2, rm[:, :n].long().unsqueeze(-1), 1.0)
+    n1h = [H] * B if n1 is None else [int(x) for x in torch.as_tensor(n1).reshape(-1).tolist()]
+    n2h = [W] * B if n2 is None else [int(x) for x in torch.as_tensor(n2).reshape(-1).tolist()]
+    masks = [None] * B if mask is None else ([mask] if matrix_input and torch.is_tensor(mask) and mask.dim() == 2 else list(mask))
+    neg = -s3.detach().to(device='cpu', dtype=torch.float32)
+    subs, rows_of, cols_of = [], [], []
+    for b in range(B):
+        if masks[b] is None:
+            rows, cols = np.arange(n1h[b]), np.arange(n2h[b])
+        else:
+            m = torch.as_tensor(masks[b]).to('cpu', torch.bool).numpy()
+            rows, cols = np.nonzero(m.any(1))[0], np.nonzero(m.any(0))[0]
+            if not np.array_equal(m, np.outer(m.any(1), m.any(0))):
+                raise ValueError('hungarian(): mask must select a row set x column set')
+        rows_of.append(rows)
+        cols_of.append(cols)
+        subs.append(neg[b].numpy()[np.ix_(rows, cols)])
+    perm = torch.zeros(B, H, W, dtype=torch.float32)
+    todo = [b for b in range(B) if subs[b].size > 0]
+    if todo:
+        flip = {b: subs[b].shape[0] > subs[b].shape[1] for b in todo}          # SciPy transposes when nr > nc
+        mats = {b: (subs[b].T if flip[b] else subs[b]) for b in todo}
+        m1 = np.asarray([mats[b].shape[0] for b in todo], np.int32)
+        m2 = np.asarray([mats[b].shape[1] for b in todo], np.int32)
+        stride = int(((m1 + 1) * (m2 + 1)).max())
+        cost = torch.zeros(len(todo), stride, dtype=torch.float32)
+        for t, b in enumerate(todo):
+            c = np.zeros((m1[t] + 1, m2[t] + 1), np.float32)
+            c[:m1[t], :m2[t]] = mats[b]
+            c[:m1[t], m2[t]] = np.inf                                             # a row is never deleted ...
+            cost[t, :c.size] = torch.from_numpy(c.reshape(-1))                    # ... a left-over column costs nothing
+        rm, _, _, _ = solver.lsape_batch(cost.to(dev), m1, m2, check=True)
+        rm = rm.cpu().numpy()
+        for t, b in enumerate(todo):
+            r, c = np.arange(m1[t]), rm[t, :m1[t]]
+            if np.any(c >= m2[t]):
+                raise ValueError('cost matrix is infeasible')
+            if flip[b]:
+                r, c = c, r
+            perm[b, rows_of[b][r], cols_of[b][c]] = 1.0
     perm = perm.to(s.device)
     return perm.squeeze(0) if matrix_input else perm
 
@@ -294,10 +328,19 @@ class GEDenv(object):
     def _host_pair(self, graph_1, graph_2):
         a1, l1, f1 = data_to_host(graph_1, self.ori_feature_dim)
         a2, l2, f2 = data_to_host(graph_2, self.ori_feature_dim)
-        if self.dataset not in AIDS_FAMILY:
-            raise NotImplementedError(f'node_metric for dataset {self.dataset} is not on the B200 path')
         cost = None
-        if l1 is None or l2 is None:
+        if self.dataset not in AIDS_FAMILY:
+            # the other node_metric tables (:235-242) compare the WHOLE feature rows and go to the kernels as an explicit
+            # node-cost matrix (ged_pairs.node_cost); weighted adjacencies (edge_attr, :170-175) are not on the B200 path
+            if getattr(graph_1, 'edge_attr', None) is not None or getattr(graph_2, 'edge_attr', None) is not None:
+                raise NotImplementedError('construct_k with edge_attr (weighted adjacency) is not on the B200 path')
+            x1 = graph_1.x.detach().to('cpu', torch.float32)
+            x2 = graph_2.x.detach().to('cpu', torch.float32)
+            pad = lambda x: torch.cat([x, x.new_zeros(1, x.shape[1])])[None]
+            cost = np.ascontiguousarray(self.node_metric(pad(x1), pad(x2))[0].numpy(), np.float32)
+            l1 = np.zeros(a1.shape[0], np.int32)
+            l2 = np.zeros(a2.shape[0], np.int32)
+        elif l1 is None or l2 is None:
             cost = node_cost_matrix(f1, f2)
             l1 = np.zeros(a1.shape[0], np.int32)
             l2 = np.zeros(a2.shape[0], np.int32)

@@ -240,6 +240,9 @@ def lsape_batch(cost: torch.Tensor, n1, n2, check: bool = False):
         n1h, n2h = np.repeat(n1h, B), np.repeat(n2h, B)
     m1, m2 = max(int(n1h.max()), 1), max(int(n2h.max()), 1)
     cost = cost.to(torch.float32).reshape(B, -1).contiguous()
+    need = (m1 + 1) * (m2 + 1)              # the C-ABI sizes its per-warp slices from (max_n1, max_n2): a ragged batch whose
+    if cost.shape[1] < need:                # largest n1 and largest n2 sit in different matrices needs the padded stride
+        cost = torch.nn.functional.pad(cost, (0, need - cost.shape[1]))
     ms = cost.shape[1]
     n1d, n2d = _as_i32(n1h, dev), _as_i32(n2h, dev)
     rm = torch.empty(B, m1, device=dev, dtype=torch.int32)

@@ -55,10 +55,12 @@ def main():
     args = ap.parse_args()
     if args.worker:
         return worker(args.work, args.reps)
-    libs = []
-    for spec in args.libs or ["prod"]:
+    libs, envs = [], {}
+    for spec in args.libs or ["prod"]:             # name[=path][@VAR=value[,VAR=value]]: a build and/or environment switches
+        spec, _, extra = spec.partition("@")
         name, _, path = spec.partition("=")
         libs.append((name, os.path.abspath(path) if path else None))
+        envs[name] = dict(kv.split("=", 1) for kv in extra.split(",") if kv)
     best = {name: {} for name, _ in libs}
     chk = {name: {} for name, _ in libs}
     for rnd in range(args.rounds):
@@ -67,6 +69,7 @@ def main():
             env.pop("GED_B200_LIBRARY", None)
             if path:
                 env["GED_B200_LIBRARY"] = path
+            env.update(envs[name])
             res = subprocess.run([sys.executable, os.path.abspath(__file__), "--worker", "--work", args.work, "--reps", str(args.reps)],
                                  env=env, capture_output=True, text=True)
             line = next((l for l in res.stdout.splitlines() if l.startswith("RESULT ")), None)

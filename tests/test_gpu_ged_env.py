@@ -6,7 +6,7 @@ import torch
 
 from oracle import ged_oracle as go
 from ppo_bihyb_b200 import ged_env, solver, synthetic
-from ppo_bihyb_b200.ged_env import GEDenv
+from ppo_bihyb_b200.ged_env import GEDenv, hungarian_ged, ipfp_ged
 from ppo_bihyb_b200.graphs import Data, FactoredK, dense_k_from_factors, label_node_cost
 
 from _golden import load, mats_of, pairs_of
@@ -45,8 +45,11 @@ def test_hungarian_square_equals_scipy(cuda_device):
     assert ged_env.hungarian(s[0]).shape == (12, 12)
     with pytest.raises(ValueError):
         ged_env.hungarian(torch.zeros(3, device=cuda_device))
-    with pytest.raises(NotImplementedError):
-        ged_env.hungarian(torch.zeros(3, 4, device=cuda_device))
+    rect = torch.from_numpy(rng.random((3, 4)).astype(np.float32))      # rectangular input (round 1 refused it)
+    row, col = opt.linear_sum_assignment(-rect.numpy())
+    want = np.zeros((3, 4), np.float32)
+    want[row, col] = 1
+    assert np.array_equal(ged_env.hungarian(rect.to(cuda_device)).cpu().numpy(), want)
 
 
 def test_invalid_cost_raises_like_scipy(cuda_device):
@@ -223,3 +226,76 @@ def test_generate_tuples_computes_and_writes_reference_format(cuda_device, tmp_p
         assert abs(want["ged"] - sols["ipfp"]) == 0.0
     again = env.generate_tuples(env.testing_graphs, 6, 2, cuda_device, cache_dir=cache, verbose=False)
     assert [t[4] for t in again] == [t[4] for t in tuples]
+
+
+def _other_metric_case(z, tag, p):
+    import torch as _t
+    n1, n2 = int(z[tag + "_n1"][p]), int(z[tag + "_n2"][p])
+    a1 = z[tag + "_adj1"][z[tag + "_adj1_off"][p]:z[tag + "_adj1_off"][p + 1]].reshape(n1, n1)
+    a2 = z[tag + "_adj2"][z[tag + "_adj2_off"][p]:z[tag + "_adj2_off"][p + 1]].reshape(n2, n2)
+    f1 = z[tag + "_feat1"][z[tag + "_f1_off"][p]:z[tag + "_f1_off"][p + 1]].reshape(n1, -1)
+    f2 = z[tag + "_feat2"][z[tag + "_f2_off"][p]:z[tag + "_f2_off"][p + 1]].reshape(n2, -1)
+    d1 = Data(x=_t.from_numpy(f1.copy()), edge_index=_t.from_numpy(np.stack(np.nonzero(a1)).astype(np.int64)))
+    d2 = Data(x=_t.from_numpy(f2.copy()), edge_index=_t.from_numpy(np.stack(np.nonzero(a2)).astype(np.int64)))
+    nk = (n1 + 1) * (n2 + 1)
+    k = z[tag + "_k"][z[tag + "_k_off"][p]:z[tag + "_k_off"][p + 1]].reshape(nk, nk)
+    xh = z[tag + "_x_hungarian"][z[tag + "_off"][p]:z[tag + "_off"][p + 1]].reshape(n1 + 1, n2 + 1)
+    return d1, d2, k, xh
+
+
+@pytest.mark.parametrize("tag,dataset", [("willow", "Willow"), ("other", "SomeOtherDataset")])
+def test_non_aids_node_metric_tables_match_reference(cuda_device, tag, dataset):
+    """node_metric's other two tables (reference ``utils/ged_env.py:235-242``: [0, VERY_LARGE_INT, 0] for CMU / Willow,
+    [0, 1, 0] otherwise; whole feature rows, ori_feature_dim = 0) reach the kernels as an explicit node-cost matrix:
+    construct_k's dense form, hungarian_ged's solution and objective equal the unmodified reference's; ipfp_ged is never
+    worse than its own Hungarian start and scores exactly on the reference's K."""
+    z = load("other_metrics")
+    env = GEDenv("ipfp", dataset, ori_feature_dim=0, device=cuda_device)
+    for p in range(len(z[tag + "_n1"])):
+        d1, d2, k_ref, xh_ref = _other_metric_case(z, tag, p)
+        n1, n2 = d1.num_nodes, d2.num_nodes
+        fk = env.construct_k(d1, d2)
+        assert np.array_equal(fk.dense().cpu().numpy(), k_ref), f"{tag} pair {p}: dense K"
+        xh = hungarian_ged(fk, n1, n2)
+        assert np.array_equal(xh.cpu().numpy(), xh_ref), f"{tag} pair {p}: hungarian_ged"
+        ged_h, _, _ = env.solve_feasible_ged(d1, d2, "hungarian")
+        assert float(ged_h) == float(z[tag + "_ged_hungarian"][p])
+        ged_i, _, _ = env.solve_feasible_ged(d1, d2, "ipfp")
+        x = ipfp_ged(fk, n1, n2)
+        k_t = torch.from_numpy(k_ref)
+        assert float(ged_i) == float(x.cpu().reshape(1, -1) @ k_t @ x.cpu().reshape(-1, 1))
+        assert float(ged_i) <= float(ged_h)
+
+
+def test_hungarian_cropping_rectangular_and_mask_equal_scipy(cuda_device):
+    """``hungarian(s, n1, n2, mask)`` (reference ``utils/ged_env.py:354-421``): per-item cropping to s[:n1, :n2] (rectangular
+    both ways), masks selecting a sub-block, 2-D and 3-D input -- against SciPy run the way ``hung_kernel`` runs it."""
+    from scipy.optimize import linear_sum_assignment
+    from ppo_bihyb_b200.ged_env import hungarian
+    rng = np.random.default_rng(12)
+    B, H, W = 24, 14, 17
+    s = torch.from_numpy(np.where(rng.random((B, H, W)) < 0.5, rng.integers(0, 4, (B, H, W)) / 3.0, rng.random((B, H, W))).astype(np.float32))
+    n1 = torch.from_numpy(rng.integers(1, H + 1, B))
+    n2 = torch.from_numpy(rng.integers(1, W + 1, B))
+    got = hungarian(s.to(cuda_device), n1, n2).cpu().numpy()
+    for b in range(B):
+        want = np.zeros((H, W), np.float32)
+        r, c = linear_sum_assignment(-s[b, :int(n1[b]), :int(n2[b])].numpy())
+        want[r, c] = 1
+        assert np.array_equal(got[b], want), f"item {b} ({int(n1[b])}x{int(n2[b])})"
+    # no cropping, 2-D input
+    r, c = linear_sum_assignment(-s[0].numpy())
+    want = np.zeros((H, W), np.float32)
+    want[r, c] = 1
+    assert np.array_equal(hungarian(s[0].to(cuda_device)).cpu().numpy(), want)
+    # mask = row set x column set
+    rows = np.sort(rng.choice(H, 6, replace=False))
+    cols = np.sort(rng.choice(W, 9, replace=False))
+    m = np.zeros((H, W), bool)
+    m[np.ix_(rows, cols)] = True
+    r, c = linear_sum_assignment(-s[1].numpy()[np.ix_(rows, cols)])
+    want = np.zeros((H, W), np.float32)
+    want[rows[r], cols[c]] = 1
+    assert np.array_equal(hungarian(s[1].to(cuda_device), mask=torch.from_numpy(m)).cpu().numpy(), want)
+    with pytest.raises(ValueError):
+        hungarian(torch.zeros(2, 2, 2, 2, device=cuda_device))
