@@ -70,7 +70,82 @@ def beam_search_batch(policy_model, ged_env, tuples: Sequence, max_actions: int,
 
 @torch.no_grad()
 def beam_search_batch_device(policy_model, ged_env, tuples: Sequence, max_actions: int, beam_size: int = 5) -> List[dict]:
-    """:func:`beam_search_batch` with the beam states resident on the device (:class:`device_env.DeviceGEDState`): the policy
+    """The whole search ON THE DEVICE, enqueued without a single host synchronisation until the results are read.
+
+    Fixed layouts, built once: P pairs x W = beam_size state slots (slot p*W + w, a validity flag each) and, per state, the
+    k*k = beam_size^2 candidates of the reference's ``idx`` order (``beam_search_step_kernel`` :15-17) -- candidate
+    c = (s*k + a)*k + b is state s with the edge (acts1[s, a], acts2[s, a, b]) toggled.  Graph sizes, labels, features, graph 2
+    and the scoring graph never change under edge toggles, so a step only moves adjacencies:
+    state -> candidates (repeat), toggle, ONE solver call over all P*W*k*k candidates, a stable descending sort of the rewards
+    per pair (ties keep candidate order, :107), candidates -> states (gather of the top W).  The probability filter (:22) is a
+    mask (reward -inf): a filtered candidate is still solved -- the call is latency-bound at this fan-out, the extra warps are
+    free -- but can never be selected.  The best tuple follows the strict-improvement rule (:108).  A pair none of whose
+    candidates survives the filter stops expanding (the reference would raise IndexError there)."""
+    from .device_env import DeviceGEDState
+    start = time.time()
+    k = W = beam_size
+    P = len(tuples)
+    env_dev = ged_env._dev(*(t[0].x for t in tuples))
+    root = DeviceGEDState(ged_env, [t[0] for t in tuples], [t[1] for t in tuples], device=env_dev)
+    dev = root.device
+    state = root.expand(W)                                  # [P*W] slots
+    cand = state.expand(k * k)                              # [P*W*k*k] candidates
+    S, C, per_pair = P * W, P * W * k * k, W * k * k
+    greedy = torch.tensor([float(t[3]) for t in tuples], device=dev)
+    valid = torch.zeros(P, W, dtype=torch.bool, device=dev)
+    valid[:, 0] = True                                      # one root state per pair
+    parent_of_cand = torch.arange(S, device=dev).repeat_interleave(k * k)
+    pair_base = (torch.arange(P, device=dev) * per_pair).unsqueeze(1)
+    hist_a = torch.zeros(S, max_actions, 2, dtype=torch.long, device=dev)       # actions / probabilities along each live beam
+    hist_p = torch.zeros(S, max_actions, 2, device=dev)
+    best_r = torch.zeros(P, device=dev)
+    best_len = torch.zeros(P, dtype=torch.long, device=dev)
+    best_a = torch.zeros(P, max_actions, 2, dtype=torch.long, device=dev)
+    best_p = torch.zeros(P, max_actions, 2, device=dev)
+    neg_inf = torch.full((), -float("inf"), device=dev)
+    for step in range(max_actions):
+        acts1, probs1, acts2, probs2 = policy_model.propose(state.batch1(), state.batch2(), k)
+        u = acts1.unsqueeze(2).expand(S, k, k).reshape(C)
+        v = acts2.reshape(C)
+        p1 = probs1.unsqueeze(2).expand(S, k, k).reshape(C)
+        p2 = probs2.reshape(C)
+        ok = valid.reshape(S).repeat_interleave(k * k) & (p1 > 1e-3) & (p2 > 1e-3)          # :22
+        cand.load_adj1(state, parent_of_cand)
+        cand.apply_edits(u, v)
+        ged = cand.solve()
+        reward = torch.where(ok, greedy.repeat_interleave(per_pair) - ged, neg_inf).view(P, per_pair)
+        top_r, top_i = torch.sort(reward, dim=1, descending=True, stable=True)               # :107
+        top_r, top_i = top_r[:, :W], top_i[:, :W]
+        gi = (top_i + pair_base).reshape(S)                                                  # global candidate of every new slot
+        src = parent_of_cand[gi]
+        new_a, new_p = hist_a[src], hist_p[src]
+        new_a[:, step, 0], new_a[:, step, 1] = u[gi], v[gi]
+        new_p[:, step, 0], new_p[:, step, 1] = p1[gi], p2[gi]
+        improve = top_r[:, 0] > best_r                                                       # :108 (strict; -inf never improves)
+        first = torch.arange(P, device=dev) * W
+        best_r = torch.where(improve, top_r[:, 0], best_r)
+        best_len = torch.where(improve, torch.full_like(best_len, step + 1), best_len)
+        best_a = torch.where(improve.view(P, 1, 1), new_a[first], best_a)
+        best_p = torch.where(improve.view(P, 1, 1), new_p[first], best_p)
+        state.load_adj1(cand, gi)                                                            # :112
+        hist_a, hist_p = new_a, new_p
+        valid = torch.isfinite(top_r)
+    cand.raise_on_error()                                   # the one synchronisation: status bits of every solve of the search
+    best_r_h, best_len_h, best_a_h, best_p_h = best_r.cpu(), best_len.cpu(), best_a.cpu(), best_p.cpu()
+    dt = (time.time() - start) / max(P, 1)
+    out = []
+    for p in range(P):
+        n = int(best_len_h[p])
+        out.append({"reward": float(best_r_h[p]), "solution": float(tuples[p][3]) - float(best_r_h[p]),
+                    "acts": [(int(a), int(b)) for a, b in best_a_h[p, :n].tolist()],
+                    "probs": [(float(a), float(b)) for a, b in best_p_h[p, :n].tolist()], "time": dt})
+    return out
+
+
+@torch.no_grad()
+def beam_search_batch_device_hostloop(policy_model, ged_env, tuples: Sequence, max_actions: int, beam_size: int = 5) -> List[dict]:
+    """Round 1's device-resident search (kept for A/B runs): states on the device, bookkeeping on the host -- two
+    device -> host copies and a Python candidate loop per step.  :func:`beam_search_batch` with the beam states resident on the device (:class:`device_env.DeviceGEDState`): the policy
     reads the states' dense batches, the candidates of a step are successor states built by an index gather + in-place
     toggles, one solver call evaluates them all, and the surviving beams are another gather.  Per step the host sees only
     the proposals (ids, probabilities) and the rewards -- two small copies -- and keeps the reference's bookkeeping."""

@@ -1258,12 +1258,26 @@ __device__ void solve_one(const SolveParams &prm, int b, int slot, const Slice &
 // MODE = kModeSmem: no tensor-memory instruction in the binary at all (a CTA of a kernel that may allocate tensor memory
 // holds the SM's allocation permit until it relinquishes it, which keeps other CTAs off the SM).
 constexpr int kMaxCtaWarps = 8;          // 4 tensor-memory warps + at most 4 shared-memory warps
+
+// Spread (latency-bound) launches give every CTA ONE candidate in the first round.  Warp w of a CTA runs on SM sub-partition
+// w % 4 (tensor memory ties a warp to the lane quarter of its sub-partition), so if that candidate always went to warp 0,
+// every active warp of an SM would share sub-partition 0 while the other three idle.  Each CTA therefore takes a ticket
+// from a per-SM counter (returned on exit, so the array is all zero between launches) and rotates its warps by it.
+#ifndef GED_SPREAD_ROTATE
+#define GED_SPREAD_ROTATE 1
+#endif
+static __device__ int g_sm_tickets[256];
 constexpr int kModeSmem = 0, kModeTmem = 1, kModeHybrid = 2;   // cost store of the CTA's warps: all shared / all tensor memory / both
 
 // S <= 3 (pairs up to 96 nodes): two 8-warp CTAs, or four 4-warp CTAs, must fit the register file -> at most 128 registers
 // per thread (registers are allocated per CTA in units of 4 warps: a 7-warp CTA at 136 registers is alone on its SM).
+#ifndef GED_TMEM_CTAS_S2
+#define GED_TMEM_CTAS_S2 0               // experiment: > 0 = launch bounds (128 threads, that many CTAs per SM) for the S <= 2 tensor-memory kernel
+#endif
+#define GED_LB_THREADS(S_, MODE_) ((GED_TMEM_CTAS_S2 > 0 && (S_) <= 2 && (MODE_) != kModeHybrid) ? 32 * kTmemWarps : 32 * kMaxCtaWarps)
+#define GED_LB_CTAS(S_, MODE_) ((GED_TMEM_CTAS_S2 > 0 && (S_) <= 2 && (MODE_) != kModeHybrid) ? GED_TMEM_CTAS_S2 : ((S_) <= 3 ? 2 : 1))
 template <int S, int MODE>
-__global__ void __launch_bounds__(32 * kMaxCtaWarps, S <= 3 ? 2 : 1) ged_solve_kernel(SolveParams prm)
+__global__ void __launch_bounds__(GED_LB_THREADS(S, MODE), GED_LB_CTAS(S, MODE)) ged_solve_kernel(SolveParams prm)
 {
     constexpr bool TM = MODE != kModeSmem;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1292,7 +1306,20 @@ __global__ void __launch_bounds__(32 * kMaxCtaWarps, S <= 3 ? 2 : 1) ged_solve_k
                                 prm.layout, m1, m2, true);
     uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16);
     asm volatile("" : "+r"(taddr));          // opaque: kept in a register instead of being re-derived from %tid per row fetch
-    for (int slot = prm.spread ? blockIdx.x + warp * gridDim.x : gwarp;;) {       // static assignment (see launch_solve_as)
+    int vwarp = warp;                        // position of this warp in the static assignment
+#if GED_SPREAD_ROTATE
+    __shared__ int ticket_slot;
+    unsigned smid = 0;
+    if (prm.spread) {
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (threadIdx.x == 0) ticket_slot = atomicAdd(&g_sm_tickets[smid & 255u], 1);
+        __syncthreads();
+        const int rot = ticket_slot % (nt > 0 ? nt : nwarps);
+        if (nt > 0) vwarp = warp < nt ? (warp + nt - rot) % nt : warp;          // rotate among the tensor-memory warps
+        else vwarp = (warp + nwarps - rot) % nwarps;
+    }
+#endif
+    for (int slot = prm.spread ? blockIdx.x + vwarp * gridDim.x : gwarp;;) {      // static assignment (see launch_solve_as)
         if (prm.work_counter) {
             if ((threadIdx.x & 31) == 0) slot = atomicAdd(prm.work_counter, 1);
             slot = __shfl_sync(kFull, slot, 0);
@@ -1319,6 +1346,12 @@ __global__ void __launch_bounds__(32 * kMaxCtaWarps, S <= 3 ? 2 : 1) ged_solve_k
         if (warp == 0)
             asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)prm.tmem_cols) : "memory");
     }
+#if GED_SPREAD_ROTATE
+    if (prm.spread) {
+        __syncthreads();                     // the ticket is held until every warp of the CTA is done
+        if (threadIdx.x == 0) atomicSub(&g_sm_tickets[smid & 255u], 1);
+    }
+#endif
 }
 
 // ---- stand-alone stages (shared-memory cost store) ----------------------------------------------------------------
@@ -1581,11 +1614,11 @@ int launch_uniform(KernelT kernel, const ParamsT &prm, int count, int slice_byte
 // backed warps, sized so that shared memory and tensor-memory columns run out together.
 struct CtaShape { int tmem_warps, tmem_cols, smem_warps, smem_bytes; };
 
-static CtaShape plan_cta(const SliceLayout &L, int max_n1, int S, int regs_per_thread)
+static CtaShape plan_cta(const SliceLayout &L, int max_n1, int S, int regs_per_thread, bool prefer_smem = false)
 {
     CtaShape c{0, 0, 1, 0};
     const int big = L.bytes + L.cost_bytes;
-    const int mode = env_int("GED_B200_COST_STORE", 2);        // 0: shared memory only, 1: tensor memory only, 2: hybrid
+    const int mode = env_int("GED_B200_COST_STORE", prefer_smem ? 0 : 2);   // 0: shared memory only, 1: tensor memory only, 2: hybrid
     int cols = 32;
     while (cols < max_n1 * S) cols <<= 1;
     const int max_warps_by_regs = 65536 / (32 * ((regs_per_thread + 7) / 8 * 8));
@@ -1612,6 +1645,10 @@ static CtaShape plan_cta(const SliceLayout &L, int max_n1, int S, int regs_per_t
     }
     // shared memory only: one warp per CTA keeps CTA granularity minimal; pack two when > 32 CTAs would fit
     c.smem_warps = (big + 1024) * 32 <= kMaxSmemBytes / 2 ? 2 : 1;
+    {
+        const int force = env_int("GED_B200_SMEM_CTA_WARPS", 0);      // experiments: shared-memory-only CTAs of this many warps
+        if (force > 0 && force <= kTmemWarps && force * big <= kMaxSmemBytes) c.smem_warps = force;
+    }
     c.smem_bytes = c.smem_warps * big;
     return c;
 }
@@ -1711,7 +1748,16 @@ int launch_solve(const SolveParams &prm, cudaStream_t stream)
     cudaFuncAttributes fa;
     const int regs = solve_regs<S>();
     if (regs < 0) return fail(GED_E_CUDA, "ged_solve_batch: cudaFuncGetAttributes failed");
-    const CtaShape c = plan_cta(prm.layout, prm.pairs.max_n1, S, regs);
+    // Latency-bound (spread) launches of the S <= 2 classes with more candidates than SMs keep the cost matrix in shared
+    // memory: measured on B200 (profiles/r02c_ab_spread_cost_store.md) a 270 / 512-candidate AIDS-30-50 step is 1.41x / 1.56x
+    // shorter than with the tensor-memory CTAs (whose four warps host one candidate each in this mode), equal at <= 1 per SM.
+    bool prefer_smem = false;
+    if (prm.spread && S <= 2) {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess)
+            prefer_smem = prm.count > sms;
+    }
+    const CtaShape c = plan_cta(prm.layout, prm.pairs.max_n1, S, regs, prefer_smem);
     if (c.smem_bytes > kMaxSmemBytes) return fail(GED_E_TOO_LARGE, "pair too large for one warp's shared-memory slice");
     if (c.tmem_warps > 0 && c.smem_warps > 0) return launch_solve_as<S, kModeHybrid>(prm, c, stream);
     return c.tmem_warps > 0 ? launch_solve_as<S, kModeTmem>(prm, c, stream) : launch_solve_as<S, kModeSmem>(prm, c, stream);

@@ -164,6 +164,27 @@ class DeviceGEDState:
         out.apply_edits(u.to(self.device), v.to(self.device))
         return out
 
+    def expand(self, repeat: int) -> "DeviceGEDState":
+        """Every state ``repeat`` times, consecutively (state s -> entries s*repeat .. s*repeat + repeat - 1).  Sizes, labels,
+        features, graph 2 and the scoring graph never change under edge toggles, so a search builds its state / candidate
+        layouts ONCE with this and afterwards only moves ``adj1`` between them (:meth:`load_adj1`) -- no host work per step."""
+        idx = torch.arange(len(self), device=self.device).repeat_interleave(repeat)
+        out = object.__new__(DeviceGEDState)
+        out.env = self.env
+        out.adj1, out.adj2, out.score1 = self.adj1[idx].contiguous(), self.adj2[idx].contiguous(), self.score1[idx].contiguous()
+        out.x1, out.x2 = self.x1[idx], self.x2[idx]
+        out.n1, out.n2, out.mask1, out.mask2 = self.n1[idx], self.n2[idx], self.mask1[idx], self.mask2[idx]
+        n1, n2 = np.repeat(self._host_n[0], repeat), np.repeat(self._host_n[1], repeat)
+        out._host_n = (n1, n2)
+        l1, o1, l2, o2 = self._lab
+        out._lab = (l1, o1[idx], l2, o2[idx])          # label pools are shared: an offset may be used by many entries
+        out._finish(self.device)
+        return out
+
+    def load_adj1(self, src: "DeviceGEDState", index: torch.Tensor) -> None:
+        """``adj1[b] = src.adj1[index[b]]`` in place (states of the same pairs: sizes and labels already agree)."""
+        torch.index_select(src.adj1, 0, index, out=self.adj1)
+
     def subset(self, idx: torch.Tensor) -> "DeviceGEDState":
         """States ``idx`` of this one, unchanged (the beams that survive a search step)."""
         zero = torch.zeros(len(idx), dtype=torch.long)

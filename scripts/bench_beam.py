@@ -23,6 +23,7 @@ ap.add_argument("--pairs", type=int, default=10)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--beam", type=int, default=3)
 ap.add_argument("--host-state", action="store_true", help="search over lists of Data graphs (GEDenv.step_batch) instead of device-resident states")
+ap.add_argument("--hostloop", action="store_true", help="round 1's device-resident search with host bookkeeping per step (A/B against the sync-free search)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
@@ -48,7 +49,10 @@ def counting_solve(self, *a, **k):
 
 
 DeviceGEDState.solve = counting_solve
-print("state:", "host lists" if args.host_state else "device resident")
+if args.hostloop:
+    from ppo_bihyb_b200 import beam_search as _bs
+    _bs.beam_search_batch_device = _bs.beam_search_batch_device_hostloop
+print("state:", "host lists" if args.host_state else ("device resident, host loop" if args.hostloop else "device resident, no host synchronisation per step"))
 print("| config | pairs | evaluate() wall s | lower-level solves | solves/s end to end | reference s/solve (1 CPU thread) | reference time for the same solves |")
 print("|---|---|---|---|---|---|---|")
 for cfg in args.configs.split(","):

@@ -113,13 +113,14 @@ def test_device_beam_search_equals_list_beam_search(cuda_device):
     torch.manual_seed(3)
     policy = ActorCritic(34, 64, False, 0, 3).to(cuda_device).eval()
     want = bs.beam_search_batch(policy, env, tuples, max_actions=3, beam_size=2)
-    got = bs.beam_search_batch_device(policy, env, tuples, max_actions=3, beam_size=2)
-    for w, g in zip(want, got):
-        assert g["reward"] == w["reward"] and g["solution"] == w["solution"]
-        if g["acts"] != w["acts"]:           # equal-reward alternatives may be ordered by probabilities that differ in the last bit
-            assert len(g["acts"]) == len(w["acts"])
-        else:
-            assert np.allclose(np.asarray(g["probs"]), np.asarray(w["probs"]), rtol=1e-4)
+    for search in (bs.beam_search_batch_device, bs.beam_search_batch_device_hostloop):     # sync-free search; round 1's host-loop search
+        got = search(policy, env, tuples, max_actions=3, beam_size=2)
+        for w, g in zip(want, got):
+            assert g["reward"] == w["reward"] and g["solution"] == w["solution"], search.__name__
+            if g["acts"] != w["acts"]:       # equal-reward alternatives may be ordered by probabilities that differ in the last bit
+                assert len(g["acts"]) == len(w["acts"])
+            else:
+                assert np.allclose(np.asarray(g["probs"]), np.asarray(w["probs"]), rtol=1e-4)
     res = bs.evaluate(policy, env, [t + ({"ipfp": t[3]}, None) for t in tuples], max_steps=2, search_size=2)
     assert set(res) == {"reward", "ratio", "solution", "gap", "num_act", "time"} and "mean" in res["solution"]
 
