@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GED_ABI_VERSION 7
+#define GED_ABI_VERSION 8
 
 /* call-level errors */
 #define GED_OK 0
@@ -105,7 +105,11 @@ typedef struct ged_solve_desc {
     /* Launch shape hint.  0: packed (CTAs filled with candidates; right when the device is busy with this or other
      * launches).  1: spread -- one candidate per CTA until every CTA slot of the device is taken (candidate = blockIdx +
      * warp * gridDim; the work queue is not used): right for a latency-bound call of a few hundred candidates in total
-     * (a rollout or beam-search step), where each solve then has an SM (almost) to itself. */
+     * (a rollout or beam-search step), where each solve then has an SM (almost) to itself.  2: team -- latency-bound call
+     * whose candidates are each solved by ALL warps of a CTA (one warp per 32 columns of the LAP, rows of K.X dealt out to the
+     * warps): the reference's per-step fan-out (<= 27 candidates per pair, ged_ppo_bihyb_eval.py:95-100; batch_size solves
+     * per rollout step, ged_ppo_bihyb_train.py:294-298) then finishes in 1/2 to 2/3 of a one-warp solve's time; pairs of up
+     * to 32 nodes are launched as with hint 1.  Results are bit-identical under every hint. */
     int32_t launch_hint;
 } ged_solve_desc;
 
@@ -130,8 +134,9 @@ typedef struct ged_solve_out {
 } ged_solve_out;
 
 /* Replaces GEDenv.step / solve_feasible_ged / ipfp_ged / hungarian_ged for a whole candidate batch
- * (utils/ged_env.py:110-158, 256-289, 303-326).  One warp per candidate; the LAP's cost matrix lives in tensor memory
- * (tcgen05.ld/st) for four warps of every CTA and in shared memory for the others. */
+ * (utils/ged_env.py:110-158, 256-289, 303-326).  Throughput launches: one warp per candidate, the LAP's cost matrix in tensor
+ * memory (tcgen05.ld/st) for four warps of every CTA and in shared memory for the others.  Latency-bound launches
+ * (launch_hint 2): one CTA per candidate, the pair staged in shared memory. */
 int ged_solve_batch(const ged_solve_desc *desc, const ged_solve_out *out, void *stream);
 
 /* Replaces hungarian_lap (utils/ged_env.py:329-351) incl. scipy's linear_sum_assignment with its exact traversal

@@ -1,8 +1,8 @@
 """Build recipe of the CUDA library (in-tree, sm_100a only): ``python ppo-bihyb_b200/build.py``.
 
-``csrc/ged_kernels.cu`` is compiled 8 times in parallel: once per slot count S (``-DGED_TU_S=S``: the solve / LSAPE / K*X
-kernels of that size class) and once for the size-independent kernels, the dispatch and the C-ABI; the objects are linked
-into ``libged_b200.so``.
+``csrc/ged_kernels.cu`` is compiled 9 times in parallel: once per slot count S (``-DGED_TU_S=S``: the solve / LSAPE / K*X
+kernels of that size class), once for the CTA-per-candidate ("team") solve kernels (``-DGED_TU_TEAM``) and once for the
+size-independent kernels, the dispatch and the C-ABI; the objects are linked into ``libged_b200.so``.
 """
 import os
 import subprocess
@@ -39,7 +39,7 @@ def build(force: bool = False, verbose: bool = False, extra=(), out: str = None)
     obj_dir = OBJ_DIR if out is None else os.path.join(OBJ_DIR, out)
     target = OUT if out is None else os.path.join(HERE, f"libged_b200.{out}.so")
     os.makedirs(obj_dir, exist_ok=True)
-    units = [("main", [])] + [(f"s{k}", [f"-DGED_TU_S={k}"]) for k in SLOT_COUNTS]
+    units = [("main", []), ("team", ["-DGED_TU_TEAM"])] + [(f"s{k}", [f"-DGED_TU_S={k}"]) for k in SLOT_COUNTS]
 
     def compile_unit(unit):
         name, defs = unit

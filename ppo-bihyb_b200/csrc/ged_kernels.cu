@@ -35,6 +35,10 @@
 // The file is compiled several times (ppo-bihyb_b200/build.py, in parallel): once per slot count S with -DGED_TU_S=S, each
 // of those translation units providing the kernels of that S behind three plain functions (launch_solve_sS, ...), and once
 // without the macro for the size-independent kernels, the dispatch and the C-ABI.
+#if !defined(GED_TU_S) && !defined(GED_TU_TEAM)
+#define GED_TU_MAIN 1                        // the translation unit with the size-independent kernels, the dispatch and the C-ABI
+#endif
+
 namespace ged_impl {
 
 constexpr unsigned kFull = 0xffffffffu;
@@ -1354,6 +1358,595 @@ __global__ void __launch_bounds__(GED_LB_THREADS(S, MODE), GED_LB_CTAS(S, MODE))
 #endif
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-PER-CANDIDATE ("team") solve for latency-bound calls: a rollout / beam-search step of a few hundred candidates
+// (reference ged_ppo_bihyb_eval.py:95-100, ged_ppo_bihyb_train.py:294-298) lasts as long as its LONGEST solve, and a
+// solve owned by one warp runs at the speed of one warp's dependent instruction stream while > 95 % of the device idles.
+// Here W = S warps of one CTA share one candidate:
+//   * LAP: warp w owns the real columns [32 w, 32 w + 32) and the deletion columns n2 + [32 w, 32 w + 32) -- one real and
+//     one deletion slot per lane instead of S of each, i.e. the scan step of the S = 1 kernel whatever the pair's size.
+//     Per scan step every warp bids its best tie-break key; the bids meet in shared memory (one STS, one CTA barrier, one
+//     128-bit LDS) and every warp continues with the same winner.  A step that has to recompute the minimum exchanges the
+//     order-preserving 64-bit image of its local minimum the same way, then the keys again.  Row duals, assignments and
+//     the cost matrix are shared (shared memory); column duals and shortest-path costs stay in the owner's registers.
+//   * K.X and the line-search update are split by ROWS over the warps (row j mod W); the reductions whose canonical order
+//     runs across rows (column sums, <K v, v>) are re-done in that order from the stored rows.
+//   * Everything that is a function of shared data only (objective, scalars, convergence test) is computed by every warp
+//     redundantly, so that control flow is uniform without broadcasts.
+// Results are bit-identical to the one-warp kernels: same arithmetic on the same operands in the same order, same scan
+// order, same tie-break keys (tests/test_gpu_team.py).  The cost matrix lives in shared memory (no tensor memory: a
+// latency-bound call has the SM's 227 KB almost to itself).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kTeamMaxW = 7;
+
+struct TeamXch {                             // exchange area of a team (one per CTA), 16-byte aligned
+    unsigned key[2][8];                      // tie-break bids of the warps, double buffered
+    unsigned long long val[2][8];            // order-preserving images of the warps' local minima, double buffered
+    int bad, status, ws_row, next;           // NaN / -inf flag of a K.X pass; per-candidate status; scratch row; work-queue slot
+};
+
+template <int W>
+__device__ __forceinline__ unsigned team_min_key(unsigned x, TeamXch *xch, int &xp)
+{
+    if ((threadIdx.x & 31) == 0) xch->key[xp][threadIdx.x >> 5] = x;
+    __syncthreads();
+    const uint4 a = *reinterpret_cast<const uint4 *>(xch->key[xp]);       // entries >= W stay at 0xffffffff
+    unsigned m = min(min(a.x, a.y), min(a.z, a.w));
+    if constexpr (W > 4) {
+        const uint4 b = *reinterpret_cast<const uint4 *>(xch->key[xp] + 4);
+        m = min(m, min(min(b.x, b.y), min(b.z, b.w)));
+    }
+    xp ^= 1;                                 // consecutive exchanges never share a buffer: one barrier per exchange is enough
+    return m;
+}
+
+template <int W>
+__device__ __forceinline__ unsigned long long team_min_val(unsigned long long x, TeamXch *xch, int &xp)
+{
+    if ((threadIdx.x & 31) == 0) xch->val[xp][threadIdx.x >> 5] = x;
+    __syncthreads();
+    unsigned long long m = xch->val[xp][0];
+#pragma unroll
+    for (int k = 1; k < W; ++k) { const unsigned long long o = xch->val[xp][k]; m = o < m ? o : m; }
+    xp ^= 1;
+    return m;
+}
+
+// LSAPE of the cost matrix in shared memory (`cost`: n1 x n2 block, row stride n2; sm.cdel: the deletion / insertion
+// entries) by the W warps of the CTA -- lsape_warp with the columns dealt out to the warps, see above.
+template <int W>
+__device__ int lsape_team(const float *cost, bool invalid, int n1, int n2, const Slice &sm, TeamXch *xch, int &xp,
+                          unsigned long long *steps_out)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int N = n1 + n2;
+    double *u = sm.u;
+    if (invalid) return GED_ST_INVALID_COST;                  // CTA-uniform
+    const int aR = lane + 32 * w;                             // this lane's real column; n2 + aR is its deletion column
+    double v[2] = {0.0, 0.0};
+    unsigned exist = 0;
+    if (aR < n2) exist |= 1u;
+    if (aR < n1) exist |= 2u;
+    for (int t = threadIdx.x; t < N; t += 32 * W) { u[t] = 0.0; sm.row4col[t] = -1; sm.col4row[t] = -1; }
+    __syncthreads();
+    const float *ccol = cost + aR;                            // element (i, aR) at ccol[i * n2]
+
+    unsigned long long steps = 0;
+    for (int cur = 0; cur < N; ++cur) {
+        double spc[2];
+        int pth[2], posk[2], kx[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int j = s ? n2 + aR : aR;
+            spc[s] = INFINITY;
+            pth[s] = -1;
+            posk[s] = (N - 1 - j) << 18;
+            int r4 = -1;
+            if ((exist >> s) & 1u) r4 = sm.row4col[j];
+            kx[s] = (((r4 >= 0) ? 512 : 511) << 18) | ((s ? W + w : w) << 14) | (lane << 9) | (r4 + 1);
+            asm volatile("" : "+r"(kx[s]));
+        }
+        unsigned live = exist;
+        double minVal = 0.0, rzmin = INFINITY;
+        int i = cur, lastk = N << 18;
+        unsigned mk;
+        int nsteps = 0;
+        bool infeasible = false;
+        bool real = i < n1;
+        double ui = u[i];
+        float cx = sm.cdel[i];
+        float cs[1] = {0.0f};
+        if (real) cs[0] = ccol[i * n2];
+
+        for (;;) {
+            ++nsteps;
+            int improved = 0;
+            unsigned lk = 0xffffffffu;
+            if (real) {                      // real row: this warp's 32 substitution entries; the deletion entry at its owner
+                LapSlots<1>::relax_row_below(spc, pth, improved, v, cs, minVal, ui, i, live);
+                const double rd = __dsub_rn(__dadd_rn(minVal, (double)cx), ui);
+                LapSlots<1>::template relax_base_below<1, 2>(spc, pth, improved, v, rd, i, (aR == i) ? live : 0u, minVal);
+            } else {                         // insertion row of column a0: its own entry at its owner + the zero block
+                const int a0 = i - n1;
+                const double ra = __dsub_rn(__dadd_rn(minVal, (double)cx), ui);
+                LapSlots<1>::template relax_base_below<0, 1>(spc, pth, improved, v, ra, i, (aR == a0) ? live : 0u, minVal);
+                const double rz = __dsub_rn(__dadd_rn(minVal, 0.0), ui);
+                if (rz < rzmin) {
+                    rzmin = rz;
+                    LapSlots<1>::template relax_base_below<1, 2>(spc, pth, improved, v, rz, i, live, minVal);
+                }
+            }
+            LapSlots<1>::min_key(lk, spc, minVal, live, posk, kx);
+            lk = improved ? 0u : lk;
+            mk = team_min_key<W>(__reduce_min_sync(kFull, lk), xch, xp);
+            if (mk - 1u >= 0xfffffffeu) {    // some value fell below minVal (bid 0) or no column attains it (all bids ~0)
+                double lmA = INFINITY, lmB = INFINITY;
+                LapSlots<1>::min_value2(lmA, lmB, spc, live);
+                const double lm = (lmB < lmA) ? lmB : lmA;
+                unsigned ohi, olo;
+                ord_from_double(lm, ohi, olo);
+                const unsigned mhi = __reduce_min_sync(kFull, ohi);
+                const unsigned mlo = __reduce_min_sync(kFull, ohi == mhi ? olo : 0xffffffffu);
+                const unsigned long long g = team_min_val<W>(((unsigned long long)mhi << 32) | mlo, xch, xp);
+                minVal = double_from_ord((unsigned)(g >> 32), (unsigned)g);
+                lk = 0xffffffffu;
+                LapSlots<1>::min_key(lk, spc, minVal, live, posk, kx);
+                mk = team_min_key<W>(__reduce_min_sync(kFull, lk), xch, xp);
+                const bool inf = (minVal == INFINITY);
+                infeasible |= inf;
+                mk = inf ? 0u : mk;
+            }
+
+            const int r4star = (int)(mk & 511u) - 1;
+            const unsigned lk_slot_bit = (((lk >> 14) & 15u) >= (unsigned)W) ? 2u : 1u;
+            {   // operands of the next row
+                const int in = max(r4star, 0);
+                real = in < n1;
+                ui = u[in];
+                cx = sm.cdel[in];
+                if (real && r4star >= 0) cs[0] = ccol[in * n2];
+            }
+            lastk -= 1 << 18;
+            const int posstark = (int)((mk & 0xfffc0000u) ^ ((mk & (512u << 18)) ? (512u << 18) : (511u << 18)));
+            live &= ~((lk == mk) ? lk_slot_bit : 0u);
+#pragma unroll
+            for (int s = 0; s < 2; ++s) posk[s] = (posk[s] == lastk) ? posstark : posk[s];
+            if (r4star < 0) break;
+            i = r4star;
+        }
+        if (infeasible) return GED_ST_INFEASIBLE;
+        steps += nsteps;
+        const int wl = (int)((mk >> 9) & 31u), ws = (int)((mk >> 14) & 15u);
+        const int sink = (ws < W) ? (wl + 32 * ws) : (n2 + wl + 32 * (ws - W));
+
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const bool scanned = ((exist & ~live) >> s) & 1u;
+            if (scanned) {
+                const int j = s ? n2 + aR : aR;
+                const double delta = __dsub_rn(minVal, spc[s]);
+                v[s] = __dsub_rn(v[s], delta);
+                const int r4 = (kx[s] & 511) - 1;
+                if (j != sink) u[r4] = __dadd_rn(u[r4], delta);          // distinct rows: every column has its own row4col
+                sm.path[j] = (int16_t)pth[s];
+            }
+        }
+        if (threadIdx.x == 0) u[cur] = __dadd_rn(u[cur], minVal);
+        __syncthreads();
+        if (threadIdx.x == 0) {              // augment along the predecessor chain
+            int j = sink;
+            for (;;) {
+                const int r = sm.path[j];
+                sm.row4col[j] = (int16_t)r;
+                const int t = sm.col4row[r];
+                sm.col4row[r] = (int16_t)j;
+                j = t;
+                if (r == cur) break;
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < n1; i += 32 * W) { const int c = sm.col4row[i]; sm.rowmatch[i] = (int16_t)(c < n2 ? c : n2); }
+    for (int a = threadIdx.x; a < n2; a += 32 * W) { const int r = sm.row4col[a]; sm.colmatch[a] = (int16_t)(r < n1 ? r : n1); }
+    __syncthreads();
+    if (steps_out) *steps_out += steps;
+    return GED_ST_OK;
+}
+
+// element (i, a) of the R x C cost matrix from where the LAP keeps it (emit_cost's routing, read back)
+__device__ __forceinline__ float team_cost_at(const float *cost, const Slice &sm, int n1, int n2, int i, int a)
+{
+    if (i < n1) return (a < n2) ? cost[i * n2 + a] : sm.cdel[i];
+    return sm.cdel[n1 + a];
+}
+
+// kv_apply by the W warps of a CTA: rows dealt out round robin; results and every rounding identical to kv_apply.
+template <int W>
+__device__ void kv_team(const Pair &P, const Slice &sm, float *rowbuf, const float *X, float *Y, const SmemCost<W> &store,
+                        float *trace, TeamXch *xch, double &s_vv_out, bool &invalid_out)
+{
+    constexpr int T = W + 1;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int R = P.R, C = P.C, n1 = P.n1, n2 = P.n2;
+    const bool fast = P.maxdeg <= kMaxDeg;
+    const int rbs = (C + 3) & ~3;
+    if (threadIdx.x == 0) xch->bad = 0;
+
+    // ---- pass A: Y = X A2^T and the row sums, row j by warp j mod W -------------------------------------------------
+    {
+        int nb2[T][kMaxDeg];
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const int a = lane + 32 * t;
+#pragma unroll
+            for (int k = 0; k < kMaxDeg; ++k) nb2[t][k] = -1;
+            if (fast && a < C) decode_neighbours(sm.bits2 + a * P.W2, P.W2, nb2[t]);
+        }
+        int par = 0;
+        for (int j = w; j < R; j += W, par ^= 1) {
+            float *buf = rowbuf + par * rbs;
+            float part = 0.0f;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const int a = lane + 32 * t;
+                if (a < C) {
+                    const float x = X[j * C + a];
+                    buf[a] = x;
+                    part = __fadd_rn(part, x);
+                }
+            }
+            part = warp_butterfly(part);
+            if (lane == 0) sm.rs[j] = part;
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const int a = lane + 32 * t;
+                if (a < C) {
+                    float in = 0.0f;
+                    if (fast) {
+#pragma unroll
+                        for (int k = 0; k < kMaxDeg; ++k) if (nb2[t][k] >= 0) in = __fadd_rn(in, buf[nb2[t][k]]);
+                    } else {
+                        for (int ww = 0; ww < P.W2; ++ww) {
+                            uint32_t word = sm.bits2[a * P.W2 + ww];
+                            while (word) { const int b = ww * 32 + __ffs(word) - 1; word &= word - 1; in = __fadd_rn(in, buf[b]); }
+                        }
+                    }
+                    Y[j * C + a] = in;
+                }
+            }
+        }
+    }
+    // column sums in the canonical order (rows ascending), 32-column tiles dealt out to the warps
+    for (int t = w; t < T; t += W) {
+        const int a = lane + 32 * t;
+        if (a < C) {
+            float s = 0.0f;
+            for (int j = 0; j < R; ++j) s = __fadd_rn(s, X[j * C + a]);
+            sm.cs[a] = s;
+        }
+    }
+    __syncthreads();                                           // Y, rs, cs complete
+    for (int i = threadIdx.x; i < R; i += 32 * W) {            // rsP[i] = sum_{j in N1(i)} rs[j]
+        float s = 0.0f;
+        for (int ww = 0; ww < P.W1; ++ww) {
+            uint32_t word = sm.bits1[i * P.W1 + ww];
+            while (word) { const int j = ww * 32 + __ffs(word) - 1; word &= word - 1; s = __fadd_rn(s, sm.rs[j]); }
+        }
+        sm.rsP[i] = s;
+    }
+    float csq[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {                              // csQ[a] = sum_{b in N2(a)} cs[b]: every warp, all tiles
+        const int a = lane + 32 * t;
+        float s = 0.0f;
+        if (a < C)
+            for (int ww = 0; ww < P.W2; ++ww) {
+                uint32_t word = sm.bits2[a * P.W2 + ww];
+                while (word) { const int b = ww * 32 + __ffs(word) - 1; word &= word - 1; s = __fadd_rn(s, sm.cs[b]); }
+            }
+        csq[t] = s;
+    }
+    __syncthreads();                                           // rsP complete
+
+    // ---- pass B: row i of the cost matrix by warp i mod W -------------------------------------------------------------
+    bool bad = false;
+    for (int i = w; i < R; i += W) {
+        int nb[kMaxDeg];
+#pragma unroll
+        for (int k = 0; k < kMaxDeg; ++k) nb[k] = -1;
+        if (fast) decode_neighbours(sm.bits1 + i * P.W1, P.W1, nb);
+        const float rsPi = sm.rsP[i];
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            if (32 * t >= C) break;
+            const int a = lane + 32 * t;
+            const bool in_row = a < C;
+            float Pv = 0.0f, T3 = 0.0f, xia = 0.0f, Qv = 0.0f;
+            if (in_row) {
+                xia = X[i * C + a];
+                Qv = Y[i * C + a];
+                if (fast) {
+                    float xv[kMaxDeg], yv[kMaxDeg];
+#pragma unroll
+                    for (int k = 0; k < kMaxDeg; ++k) {
+                        xv[k] = 0.0f;
+                        yv[k] = 0.0f;
+                        if (nb[k] >= 0) { xv[k] = X[nb[k] * C + a]; yv[k] = Y[nb[k] * C + a]; }
+                    }
+#pragma unroll
+                    for (int k = 0; k < kMaxDeg; ++k)
+                        if (nb[k] >= 0) { Pv = __fadd_rn(Pv, xv[k]); T3 = __fadd_rn(T3, yv[k]); }
+                } else {
+                    for (int ww = 0; ww < P.W1; ++ww) {
+                        uint32_t word = sm.bits1[i * P.W1 + ww];
+                        while (word) {
+                            const int j = ww * 32 + __ffs(word) - 1;
+                            word &= word - 1;
+                            Pv = __fadd_rn(Pv, X[j * C + a]);
+                            T3 = __fadd_rn(T3, Y[j * C + a]);
+                        }
+                    }
+                }
+            }
+            const float t1 = (a < n2) ? __fsub_rn(rsPi, Pv) : rsPi;
+            const float t2 = (i < n1) ? __fsub_rn(csq[t], Qv) : csq[t];
+            float sres = __fadd_rn(t1, t2);
+            sres = __fsub_rn(sres, __fadd_rn(T3, T3));
+            const float d = in_row ? __fmul_rn(node_cost_at(P, sm, i, a), xia) : 0.0f;
+            const float c = __fadd_rn(sres, d);
+            emit_cost<W>(store, sm, n1, n2, i, t, c);
+            if (in_row) {
+                if (!(i == n1 && a == n2)) bad |= (c != c) || (c == -INFINITY);
+                if (trace) trace[i * C + a] = c;
+            }
+        }
+    }
+    if (__any_sync(kFull, bad) && lane == 0) atomicOr(&xch->bad, 1);
+    __syncthreads();                                           // cost matrix complete
+    invalid_out = xch->bad != 0;
+    // s_vv = <cost, X> in the canonical order (per lane: rows ascending, tiles ascending; fp64), by every warp
+    double svv = 0.0;
+    for (int i = 0; i < R; ++i) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            if (32 * t >= C) break;
+            const int a = lane + 32 * t;
+            if (a < C) svv = __dadd_rn(svv, __dmul_rn((double)team_cost_at(store.base, sm, n1, n2, i, a), (double)X[i * C + a]));
+        }
+    }
+    s_vv_out = warp_butterfly(svv);
+}
+
+// One candidate solve by the W warps of a CTA (solve_one for a team).
+template <int W>
+__device__ void solve_team(const SolveParams &prm, int b, const Slice &sm, float *rowbuf, TeamXch *xch, int &xp)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nthr = 32 * W;
+    const ged_solve_out &out = prm.out;
+    const int p = prm.base_idx ? prm.base_idx[b] : b;
+    const SmemCost<W> store{sm.cost, prm.pairs.n2[p]};
+    Pair P;
+    if (threadIdx.x == 0) xch->status = 0;
+    __syncthreads();
+    if (w == 0) {
+        int st = 0;
+        load_pair(prm.pairs, p, sm, P, st);
+        if (st && lane == 0) xch->status = st;
+    }
+    __syncthreads();
+    {   // the scalars of the pair, by every warp (load_pair filled shared memory)
+        const ged_pairs &pp = prm.pairs;
+        P.n1 = pp.n1[p];
+        P.n2 = pp.n2[p];
+        P.R = P.n1 + 1;
+        P.C = P.n2 + 1;
+        P.N = P.n1 + P.n2;
+        P.W1 = (P.n1 + 31) / 32 > 0 ? (P.n1 + 31) / 32 : 1;
+        P.W2 = (P.n2 + 31) / 32 > 0 ? (P.n2 + 31) / 32 : 1;
+        P.node_cost = pp.node_cost ? pp.node_cost + pp.node_cost_off[p] : nullptr;
+    }
+    int status = xch->status;
+    const int n1 = P.n1, n2 = P.n2;
+
+    // GEDenv.step edge toggle (ged_env.py:110-121)
+    const int eu = prm.edit_u ? prm.edit_u[b] : -1, ev = prm.edit_v ? prm.edit_v[b] : -1;
+    const bool has_edit = eu >= 0 && ev >= 0 && eu != ev && eu < n1 && ev < n1;
+    bool was_present = false;
+    if (has_edit) {
+        was_present = bit_at(sm.bits1, P.W1, eu, ev) || bit_at(sm.bits1, P.W1, ev, eu);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t m_uv = 1u << (ev & 31), m_vu = 1u << (eu & 31);
+            uint32_t &w_uv = sm.bits1[eu * P.W1 + (ev >> 5)];
+            w_uv = was_present ? (w_uv & ~m_uv) : (w_uv | m_uv);
+            uint32_t &w_vu = sm.bits1[ev * P.W1 + (eu >> 5)];
+            w_vu = was_present ? (w_vu & ~m_vu) : (w_vu | m_vu);
+        }
+        __syncthreads();
+    }
+    P.maxdeg = max_degree(sm.bits1, P.R, P.W1, sm.bits2, P.C, P.W2);
+    const int nnz1 = count_bits(sm.bits1, P.R * P.W1), nnz2 = count_bits(sm.bits2, P.C * P.W2);
+
+    // scratch row for X and Y = X A2^T (global, L2 resident): claimed by one thread
+    if (threadIdx.x == 0) {
+        int h = b;
+        if (prm.workspace && prm.ws_slots > 0) {
+            h = blockIdx.x % prm.ws_slots;
+            while (atomicCAS(prm.ws_locks + h, 0, 1) != 0) h = (h + 1 == prm.ws_slots) ? 0 : h + 1;
+        }
+        xch->ws_row = h;
+    }
+    __syncthreads();
+    const int ws_row = xch->ws_row;
+    float *X = prm.workspace ? prm.workspace + (long long)ws_row * 2 * prm.ws_stride : nullptr;
+    float *Y = X ? X + prm.ws_stride : nullptr;
+    unsigned long long lap_steps = 0;
+    int iters = 0;
+    double best_ub = INFINITY;
+
+    if (status == 0) {
+        if (prm.x_init) {
+            const float *x0 = prm.x_init + (long long)b * prm.mat_stride;
+            for (int e = threadIdx.x; e < P.R * P.C; e += nthr) X[e] = x0[e];
+            for (int i = threadIdx.x; i < n1; i += nthr) sm.bestrow[i] = (int16_t)n2;
+            for (int a = threadIdx.x; a < n2; a += nthr) sm.bestcol[a] = (int16_t)n1;
+            __syncthreads();
+        } else {
+            // hungarian_ged (ged_env.py:303-326): v0 = LSAPE(node_cost_mat); the closed form is cheap: warp 0 alone
+            if (w == 0) init_cost_closed_form<W>(P, sm, store, out.tr_init_cost ? out.tr_init_cost + (long long)b * prm.mat_stride : nullptr);
+            __syncthreads();
+            status |= lsape_team<W>(store.base, false, n1, n2, sm, xch, xp, &lap_steps);
+            if (status == 0) {
+                for (int i = threadIdx.x; i < n1; i += nthr) {
+                    sm.bestrow[i] = sm.rowmatch[i];
+                    if (out.tr_init_rowmatch) out.tr_init_rowmatch[(long long)b * out.match_stride_1 + i] = sm.rowmatch[i];
+                }
+                for (int a = threadIdx.x; a < n2; a += nthr) {
+                    sm.bestcol[a] = sm.colmatch[a];
+                    if (out.tr_init_colmatch) out.tr_init_colmatch[(long long)b * out.match_stride_2 + a] = sm.colmatch[a];
+                }
+                if (prm.solver_kind == GED_SOLVER_IPFP)
+                    for (int i = w; i < P.R; i += W)
+                        for (int a = lane; a < P.C; a += 32) X[i * P.C + a] = dense_b(P, sm.rowmatch, sm.colmatch, i, a);
+                __syncthreads();
+            }
+        }
+    }
+
+    if (status == 0 && prm.solver_kind == GED_SOLVER_IPFP) {
+        for (int it = 0; it < prm.max_iter; ++it) {
+            iters = it + 1;
+            double s_vv;
+            bool invalid;
+            kv_team<W>(P, sm, rowbuf, X, Y, store, out.tr_cost ? out.tr_cost + ((long long)b * prm.max_iter + it) * prm.mat_stride : nullptr,
+                       xch, s_vv, invalid);                                                    // ged_env.py:269
+            status |= lsape_team<W>(store.base, invalid, n1, n2, sm, xch, xp, &lap_steps);      // :270
+            if (status != 0) break;
+            // scalars: functions of shared data only -> every warp computes them, control flow stays uniform
+            const double ub = score_assignment(P, sm, nnz1, nnz2, sm.rowmatch, sm.colmatch);   // :271
+            const bool better = ub < best_ub;                                                 // :272-274
+            if (better) best_ub = ub;
+            const double s_vb = matched_cost_sum<W>(store, sm, n1, n2);
+            const double alpha = __dsub_rn(s_vb, s_vv);                                        // :275
+            const double beta = __dadd_rn(__dsub_rn(ub, __dadd_rn(s_vb, s_vb)), s_vv);         // :277
+            const double t0 = __ddiv_rn(-alpha, beta);                                         // :278
+            const float t0f = (float)t0;
+            const bool jump = (beta <= 0.0) || (t0f >= 1.0f);                                  // :279
+            if (better && w == 0) {
+                for (int i = lane; i < n1; i += 32) sm.bestrow[i] = sm.rowmatch[i];
+                for (int a = lane; a < n2; a += 32) sm.bestcol[a] = sm.colmatch[a];
+            }
+            float *trx = out.tr_x_after ? out.tr_x_after + ((long long)b * prm.max_iter + it) * prm.mat_stride : nullptr;
+            for (int i = w; i < P.R; i += W) {
+                const int rm = (i < n1) ? sm.rowmatch[i] : -1;
+                for (int a = lane; a < P.C; a += 32) {
+                    const int e = i * P.C + a;
+                    const float bv = (i < n1) ? ((rm == a) ? 1.0f : 0.0f) : ((a < n2 && sm.colmatch[a] == n1) ? 1.0f : 0.0f);
+                    float xn;
+                    if (jump) xn = bv;                                                         // :280
+                    else { const float x = X[e]; xn = __fadd_rn(x, __fmul_rn(t0f, __fsub_rn(bv, x))); }   // :282
+                    X[e] = xn;
+                    if (trx) trx[e] = xn;
+                }
+            }
+            if (w == 0) {
+                if (out.tr_scalars && lane == 0) {
+                    double *d = out.tr_scalars + ((long long)b * prm.max_iter + it) * 6;
+                    d[0] = s_vv; d[1] = s_vb; d[2] = ub; d[3] = alpha; d[4] = beta; d[5] = t0;
+                }
+                if (out.tr_rowmatch)
+                    for (int i = lane; i < n1; i += 32) out.tr_rowmatch[((long long)b * prm.max_iter + it) * out.match_stride_1 + i] = sm.rowmatch[i];
+                if (out.tr_colmatch)
+                    for (int a = lane; a < n2; a += 32) out.tr_colmatch[((long long)b * prm.max_iter + it) * out.match_stride_2 + a] = sm.colmatch[a];
+            }
+            __syncthreads();                                     // X rows of the other warps, bestrow / bestcol
+            if (fabs(__dsub_rn(s_vv, s_vb)) / s_vv < 1e-3) break;                              // :284-285
+        }
+    }
+    __syncthreads();
+
+    // scoring on the edited pair and on the base pair (ged_env.py:122,158) and the outputs: warp 0
+    if (w == 0) {
+        float ged_edit = NAN, ged_base = NAN;
+        if (status == 0) {
+            ged_edit = (float)score_assignment(P, sm, nnz1, nnz2, sm.bestrow, sm.bestcol);
+            ged_base = ged_edit;
+            if (prm.score_adj1) {
+                __syncwarp();
+                const bool bad = load_bits(prm.score_adj1 + prm.score_adj1_off[prm.score_idx[b]], n1, prm.score_ld, P.W1, sm.bits1, lane);
+                __syncwarp();
+                if (bad) status |= GED_ST_BAD_GRAPH;
+                const int nnz1o = count_bits(sm.bits1, P.R * P.W1);
+                ged_base = bad ? NAN : (float)score_assignment(P, sm, nnz1o, nnz2, sm.bestrow, sm.bestcol);
+            } else if (has_edit) {
+                __syncwarp();
+                if (lane == 0) {
+                    const uint32_t m_uv = 1u << (ev & 31), m_vu = 1u << (eu & 31);
+                    uint32_t &w_uv = sm.bits1[eu * P.W1 + (ev >> 5)];
+                    w_uv = was_present ? (w_uv | m_uv) : (w_uv & ~m_uv);
+                    uint32_t &w_vu = sm.bits1[ev * P.W1 + (eu >> 5)];
+                    w_vu = was_present ? (w_vu | m_vu) : (w_vu & ~m_vu);
+                }
+                __syncwarp();
+                ged_base = (float)score_assignment(P, sm, nnz1 + (was_present ? 2 : -2), nnz2, sm.bestrow, sm.bestcol);
+            }
+        }
+        if (lane == 0) {
+            out.ged[b] = ged_base;
+            if (out.ged_edited) out.ged_edited[b] = ged_edit;
+            if (out.iters) out.iters[b] = iters;
+            if (out.status) out.status[b] = status;
+            if (out.tr_lap_steps) out.tr_lap_steps[b] = lap_steps;
+        }
+        if (prm.workspace && prm.ws_slots > 0) {
+            __syncwarp();
+            if (lane == 0) { __threadfence(); atomicExch(prm.ws_locks + ws_row, 0); }
+        }
+        if (status == 0) {
+            for (int i = lane; i < n1; i += 32) out.rowmatch[(long long)b * out.match_stride_1 + i] = sm.bestrow[i];
+            for (int a = lane; a < n2; a += 32) out.colmatch[(long long)b * out.match_stride_2 + a] = sm.bestcol[a];
+            if (out.x_out) {
+                float *xo = out.x_out + (long long)b * prm.mat_stride;
+                for (int i = 0; i < P.R; ++i)
+                    for (int a = lane; a < P.C; a += 32) xo[i * P.C + a] = dense_b(P, sm.bestrow, sm.bestcol, i, a);
+            }
+        }
+    }
+    __syncthreads();                                             // the slice is reused by the CTA's next candidate
+}
+
+// Dynamic shared memory of a team CTA: [slice][cost block][W double-buffered X rows][exchange area]
+__host__ __device__ inline int team_rowbuf_bytes(int max_n2) { return 2 * 4 * align_up(max_n2 + 1, 4); }
+__host__ __device__ inline int team_smem_bytes(const SliceLayout &L, int W, int max_n2)
+{
+    return L.bytes + L.cost_bytes + W * team_rowbuf_bytes(max_n2) + (int)sizeof(TeamXch);
+}
+
+template <int W>
+__global__ void __launch_bounds__(32 * W) ged_solve_team_kernel(SolveParams prm)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int w = threadIdx.x >> 5;
+    const int m1 = prm.pairs.max_n1, m2 = prm.pairs.max_n2;
+    const Slice sm = carve(smem_raw, prm.layout, m1, m2, true);
+    float *rowbuf = reinterpret_cast<float *>(smem_raw + prm.layout.bytes + prm.layout.cost_bytes + w * team_rowbuf_bytes(m2));
+    TeamXch *xch = reinterpret_cast<TeamXch *>(smem_raw + prm.layout.bytes + prm.layout.cost_bytes + W * team_rowbuf_bytes(m2));
+    if (threadIdx.x < 16) xch->key[threadIdx.x >> 3][threadIdx.x & 7] = 0xffffffffu;
+    __syncthreads();
+    int xp = 0;
+    for (int slot = blockIdx.x;; slot += gridDim.x) {
+        if (prm.work_counter) {                  // persistent CTAs pulling candidates (longest first) from the work queue
+            if (threadIdx.x == 0) xch->next = atomicAdd(prm.work_counter, 1);
+            __syncthreads();
+            slot = xch->next;
+        }
+        if (slot >= prm.count) break;
+        const int b = prm.order ? prm.order[slot] : slot;
+        solve_team<W>(prm, b, sm, rowbuf, xch, xp);
+    }
+}
+
 // ---- stand-alone stages (shared-memory cost store) ----------------------------------------------------------------
 struct LsapeParams {
     int B;
@@ -1432,7 +2025,7 @@ __global__ void ged_kv_kernel(KvParams prm)
                 prm.cost + (long long)b * prm.mat_stride, s_vv, invalid);         // the result is taken from the trace hook
 }
 
-#ifndef GED_TU_S
+#ifdef GED_TU_MAIN
 struct ScoreParams {
     ged_pairs pairs;
     int B;
@@ -1577,7 +2170,7 @@ __global__ void __launch_bounds__(kSinkhornThreads) ged_sinkhorn_kernel(const in
     }
 }
 
-#endif  // !GED_TU_S
+#endif  // GED_TU_MAIN
 
 // ---------------------------------------------------------------------------------------------------------------
 // Host side
@@ -1763,6 +2356,46 @@ int launch_solve(const SolveParams &prm, cudaStream_t stream)
     return c.tmem_warps > 0 ? launch_solve_as<S, kModeTmem>(prm, c, stream) : launch_solve_as<S, kModeSmem>(prm, c, stream);
 }
 
+// ---- team (CTA-per-candidate) launches: their own translation unit (-DGED_TU_TEAM) --------------------------------------
+int launch_solve_team(int W, const SolveParams &prm, cudaStream_t stream);
+
+#ifdef GED_TU_TEAM
+template <int W>
+int launch_team(SolveParams prm, cudaStream_t stream)
+{
+    const int smem = team_smem_bytes(prm.layout, W, prm.pairs.max_n2);
+    if (smem > kMaxSmemBytes) return fail(GED_E_TOO_LARGE, "pair too large for a team CTA's shared memory");
+    cudaError_t e = cudaFuncSetAttribute(ged_solve_team_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail_cuda(e, "ged_solve_batch (team)");
+    int per_sm = 0, dev = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ged_solve_team_kernel<W>, 32 * W, smem) != cudaSuccess || per_sm < 1 ||
+        cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return fail(GED_E_CUDA, "ged_solve_batch (team): device query failed");
+    int grid = prm.count < sms * per_sm ? prm.count : sms * per_sm;      // persistent CTAs beyond one wave
+    if (prm.ws_slots > 0 && grid > prm.ws_slots) grid = prm.ws_slots;    // one scratch row per CTA in flight
+    if (env_int("GED_B200_VERBOSE", 0))
+        fprintf(stderr, "[ged_b200] team solve<W=%d> count=%d max_n=(%d,%d) grid=%d (%d CTAs/SM), %d B dynamic smem\n", W, prm.count,
+                prm.pairs.max_n1, prm.pairs.max_n2, grid, per_sm, smem);
+    ged_solve_team_kernel<W><<<grid, 32 * W, smem, stream>>>(prm);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(e, "ged_solve_batch (team)");
+    return GED_OK;
+}
+
+int launch_solve_team(int W, const SolveParams &prm, cudaStream_t stream)
+{
+    switch (W) {
+    case 2: return launch_team<2>(prm, stream);
+    case 3: return launch_team<3>(prm, stream);
+    case 4: return launch_team<4>(prm, stream);
+    case 5: return launch_team<5>(prm, stream);
+    case 6: return launch_team<6>(prm, stream);
+    case 7: return launch_team<7>(prm, stream);
+    default: return fail(GED_E_BADARG, "team launch: 2..7 warps");
+    }
+}
+#endif  // GED_TU_TEAM
+
 // ---- per-S entry points (one translation unit each) and their dispatch ---------------------------------------------------
 #define GED_CAT_(a, b) a##b
 #define GED_CAT(a, b) GED_CAT_(a, b)
@@ -1793,7 +2426,7 @@ int GED_CAT(launch_kv_s, GED_TU_S)(const KvParams &prm, cudaStream_t stream)
 {
     return launch_uniform(ged_kv_kernel<GED_TU_S>, prm, prm.pairs.num_pairs, prm.layout.bytes + prm.layout.cost_bytes, stream, "ged_kv_batch");
 }
-#else
+#elif defined(GED_TU_MAIN)
 thread_local char g_err[512] = "";
 
 #define GED_DISPATCH_S(S_, NAME, ...)                                                                   \
@@ -1824,11 +2457,11 @@ static int dispatch_solve(int S, const SolveParams &prm, cudaStream_t stream) { 
 static int dispatch_lsape(int S, const LsapeParams &prm, cudaStream_t stream) { GED_DISPATCH_S(S, launch_lsape_s, prm, stream) }
 static int dispatch_kv(int S, const KvParams &prm, cudaStream_t stream) { GED_DISPATCH_S(S, launch_kv_s, prm, stream) }
 static int dispatch_resident(int S, const SliceLayout &L, int max_n1) { GED_DISPATCH_S(S, resident_solve_s, L, max_n1) }
-#endif  // GED_TU_S
+#endif  // GED_TU_S / GED_TU_MAIN
 
 }  // namespace ged_impl
 
-#ifndef GED_TU_S
+#ifdef GED_TU_MAIN
 using namespace ged_impl;
 
 extern "C" {
@@ -1872,14 +2505,18 @@ int ged_solve_batch(const ged_solve_desc *d, const ged_solve_out *o, void *strea
     prm.order = d->order;
     prm.count = d->order ? d->order_count : d->B;
     prm.work_counter = d->work_counter;
-    prm.spread = d->launch_hint == 1 && env_int("GED_B200_SPREAD", 1);
+    prm.spread = d->launch_hint >= 1 && env_int("GED_B200_SPREAD", 1);
     if (prm.count < 0 || prm.count > d->B) return fail(GED_E_BADARG, "ged_solve_batch: order_count out of range");
     if (prm.count == 0) return GED_OK;
     prm.tmem_warps = 0;
     prm.tmem_cols = 0;
     prm.out = *o;
     prm.layout = make_layout(d->pairs.max_n1, d->pairs.max_n2);
-    return dispatch_solve(slots_for(d->pairs.max_n1, d->pairs.max_n2), prm, (cudaStream_t)stream);
+    const int S = slots_for(d->pairs.max_n1, d->pairs.max_n2);
+    // launch_hint 2: a latency-bound call -- the W = S warps of a CTA share one candidate (team kernel); pairs of up to 32
+    // nodes (one slot per lane already) and builds without it take the spread launch.
+    if (d->launch_hint == 2 && S >= 2 && S <= kTeamMaxW && env_int("GED_B200_TEAM", 1)) return launch_solve_team(S, prm, (cudaStream_t)stream);
+    return dispatch_solve(S, prm, (cudaStream_t)stream);
 }
 
 int ged_lsape_batch(int32_t B, const int32_t *n1, const int32_t *n2, int32_t max_n1, int32_t max_n2,
@@ -1999,8 +2636,8 @@ int64_t ged_solve_smem_bytes(int32_t max_n1, int32_t max_n2)
 }
 
 int ged_abi_version(void) { return GED_ABI_VERSION; }
-const char *ged_version(void) { return "ged_b200 0.4.0 (sm_100a; ABI 7; canonical order v2; tensor-memory cost store; persistent work-queue launches)"; }
+const char *ged_version(void) { return "ged_b200 0.5.0 (sm_100a; ABI 8; canonical order v2; tensor-memory cost store; persistent work-queue launches; CTA-per-candidate team launches)"; }
 const char *ged_last_error(void) { return g_err; }
 
 }  // extern "C"
-#endif  // !GED_TU_S
+#endif  // GED_TU_MAIN

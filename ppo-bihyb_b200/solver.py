@@ -16,6 +16,15 @@ SOLVERS = {"ipfp": _lib.GED_SOLVER_IPFP, "hungarian": _lib.GED_SOLVER_HUNGARIAN}
 
 # calls of at most this many candidates in total are latency-bound (a rollout / beam-search step): one candidate per CTA
 SPREAD_MAX_CANDIDATES = 512
+# ... and of at most this many are solved by one CTA each (all warps of the CTA share the candidate: launch_hint 2)
+TEAM_MAX_CANDIDATES = int(os.environ.get("GED_B200_TEAM_MAX", "512"))
+
+
+def launch_hint_for(total_candidates: int) -> int:
+    """``ged_solve_desc.launch_hint`` for a call of this many candidates in total (include/ged_b200.h)."""
+    if total_candidates <= TEAM_MAX_CANDIDATES:
+        return 2
+    return 1 if total_candidates <= SPREAD_MAX_CANDIDATES else 0
 
 
 def _stream(device) -> int:
@@ -101,14 +110,15 @@ def solve_batch(pairs: PairSet, base_idx=None, edit_u=None, edit_v=None, solver:
                 x_init: Optional[torch.Tensor] = None, dense_x: bool = False, trace: bool = False,
                 check: bool = False, score_adj1: Optional[torch.Tensor] = None,
                 score_adj1_off: Optional[torch.Tensor] = None, score_idx=None, size_classes: bool = True,
-                plan=None, score_adj1_ld: int = 0, lap_steps: bool = False) -> SolveResult:
+                plan=None, score_adj1_ld: int = 0, lap_steps: bool = False, launch_hint: Optional[int] = None) -> SolveResult:
     """All candidate solves of one batch (``ged_solve_batch``): one launch per size class, concurrently on side
     streams, results in candidate order.
 
     Candidate b = base pair ``base_idx[b]`` with edge ``(edit_u[b], edit_v[b])`` of graph 1 toggled
     (reference ``GEDenv.step``, ``utils/ged_env.py:110-124``).  ``plan`` = a cached ``(order_device, classes)`` from
     :func:`make_plan` avoids re-planning when the same candidate list is solved repeatedly.  ``lap_steps`` also returns the
-    number of LAP scan steps every solve executed (``result.trace["lap_steps"]``; the work figure of the roofline)."""
+    number of LAP scan steps every solve executed (``result.trace["lap_steps"]``; the work figure of the roofline).
+    ``launch_hint`` overrides the launch shape chosen from the call's size (0 packed, 1 spread, 2 team; tests / A-B runs)."""
     lib = _lib.require_cuda()
     if solver not in SOLVERS:
         raise NotImplementedError(f"{solver} is not implemented.")      # reference ged_env.py:156
@@ -163,7 +173,7 @@ def solve_batch(pairs: PairSet, base_idx=None, edit_u=None, edit_v=None, solver:
                              p(score_adj1, _lib.c_u8p), p(score_adj1_off, _lib.c_i64p), p(score_idx, _lib.c_i32p),
                              int(score_adj1_ld), int(max_iter), SOLVERS[solver], p(x_init, _lib.c_f32p), ms, p(workspace, _lib.c_f32p),
                              p(locks, _lib.c_i32p), 0, 0, p(None, _lib.c_i32p), 0, p(None, _lib.c_i32p),
-                             1 if B <= SPREAD_MAX_CANDIDATES else 0)
+                             launch_hint_for(B) if launch_hint is None else int(launch_hint))
 
     def set_region(k):
         if counters is not None:
