@@ -2367,10 +2367,24 @@ int launch_team(SolveParams prm, cudaStream_t stream)
     if (smem > kMaxSmemBytes) return fail(GED_E_TOO_LARGE, "pair too large for a team CTA's shared memory");
     cudaError_t e = cudaFuncSetAttribute(ged_solve_team_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail_cuda(e, "ged_solve_batch (team)");
-    int per_sm = 0, dev = 0, sms = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ged_solve_team_kernel<W>, 32 * W, smem) != cudaSuccess || per_sm < 1 ||
-        cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         return fail(GED_E_CUDA, "ged_solve_batch (team): device query failed");
+    {   // Shared-memory carve-out.  An SM runs CTAs of ONE L1 / shared split at a time and the driver's own choice follows the
+        // single CTA: measured on B200 (profiles/r02d_team.md) a 270-candidate beam step (two size classes launched side by side)
+        // takes 108 ms with the driver's choice against 58 ms at 50 % (89 ms with one warp per candidate).  Half of the array is
+        // the default -- the K.X gathers of X and Y (global, L2 resident) want the other half as L1: 50 % is 3-8 % faster than
+        // the maximum -- unless the CTAs of the whole call (prm.B candidates over all its size-class launches) need more to be
+        // resident together.
+        const int per_sm_needed = (prm.B + sms - 1) / sms;
+        const int dflt = per_sm_needed * (smem + 1024) <= kSmemPerSm / 2 ? 50 : 100;
+        const int carve = env_int("GED_B200_TEAM_CARVEOUT", dflt);
+        e = cudaFuncSetAttribute(ged_solve_team_kernel<W>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        if (e != cudaSuccess) return fail_cuda(e, "ged_solve_batch (team)");
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ged_solve_team_kernel<W>, 32 * W, smem) != cudaSuccess || per_sm < 1)
+        return fail(GED_E_CUDA, "ged_solve_batch (team): occupancy query failed");
     int grid = prm.count < sms * per_sm ? prm.count : sms * per_sm;      // persistent CTAs beyond one wave
     if (prm.ws_slots > 0 && grid > prm.ws_slots) grid = prm.ws_slots;    // one scratch row per CTA in flight
     if (env_int("GED_B200_VERBOSE", 0))
