@@ -395,6 +395,37 @@ def main():
     barrier()
     assert np.array_equal(ged_host.numpy(), res.ged.cpu().numpy()), "host-buffer path and device path disagree"
 
+    # ---- the reference's own call sizes (latency-bound): one beam-search step (10 pairs x 27 candidates, ged_ppo_bihyb_eval.py:95-100)
+    # and one rollout step (32 pairs x 1 edit, ged_ppo_bihyb_train.py:294-298) of the same workload, device-timed, with the
+    # launch shape the host layer picks for that size (CTA-per-candidate "team" kernel) and with one warp per candidate ------------
+    latency = None
+    if rank == 0:
+        from ppo_bihyb_b200 import synthetic
+        latency = {}
+        for name, npairs, nedits in (("beam_step_10x27", 10, 27), ("rollout_step_32x1", 32, 1)):
+            lp = synthetic.make_pairs(args.config, npairs, seed_offset=100)
+            lb, lu, lv = synthetic.make_edits(lp, nedits, seed_offset=100)
+            lps = PairSet.from_host(lp, dev)
+            lplan = solver.make_plan(lps, lb)
+            row = {"candidates": int(len(lb))}
+            for label, hint in (("ms", None), ("ms_one_warp_per_candidate", 1)):
+                best = None
+                for rep in range(3):
+                    flush.fill_(1)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    r = solver.solve_batch(lps, base_idx=lb, edit_u=lu, edit_v=lv, max_iter=args.max_iter, plan=lplan, launch_hint=hint)
+                    e1.record()
+                    e1.synchronize()
+                    if rep:
+                        best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
+                row[label] = best
+                row.setdefault("checksum", float(r.ged.double().sum()))
+                assert row["checksum"] == float(r.ged.double().sum()), "launch shapes disagree"
+            row["solves_per_s"] = row["candidates"] / (row["ms"] * 1e-3)
+            latency[name] = row
+    barrier()
+
     tmax = torch.tensor([ms_total, sum(e2e_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -427,6 +458,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host_batch.h2d_bytes,
                     "d2h_bytes_per_step": host_batch.d2h_bytes, "ms_per_step": e2e_total / args.steps},
             "gpu_launches": launches,
+            "latency_regime": latency,
             "clocks": clocks,
             "roofline": roof,
         }

@@ -194,8 +194,9 @@ class ActorNet(nn.Module):
             rows = torch.arange(len(prev_act), device=state_feat.device)
             act_query = torch.tanh(self.act2_query(state_feat[rows, prev_act, :]))
             act_scores = (act_query.unsqueeze(1) * state_feat).sum(dim=-1)
-            mask = torch.zeros_like(act_scores)
-            mask[rows, prev_act] = -float("inf")
+            # scatter_ takes the scalar as a kernel argument (an indexed assignment of a Python float copies it from pageable
+            # host memory: not capturable in a CUDA graph)
+            mask = torch.zeros_like(act_scores).scatter_(1, prev_act.unsqueeze(1), -float("inf"))
         mask = mask.masked_fill(~node_mask, -float("inf"))
         act_probs = torch.softmax(act_scores + mask, dim=1)
         if greedy_sel_num > 0:
@@ -211,7 +212,9 @@ class ActorNet(nn.Module):
         out = []
         prev = None
         for step in range(2):
-            dist = Categorical(probs=self.select_nodes(state_feat, node_mask, 0, prev_act=prev))
+            # validate_args=False: the constraint check reads a flag back to the host (a synchronisation per call, and not
+            # capturable in a CUDA graph); the probabilities are a masked soft-max
+            dist = Categorical(probs=self.select_nodes(state_feat, node_mask, 0, prev_act=prev), validate_args=False)
             act = dist.sample() if known_action[step] is None else known_action[step]
             out.append((act, dist.log_prob(act), dist.entropy()))
             prev = act

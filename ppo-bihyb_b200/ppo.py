@@ -10,6 +10,7 @@ encoder at lr/10), rollout loop :270-321.  What is different:
     one NCCL call per epoch on a flat gradient bucket the parameters' ``.grad`` are views of -- the only inter-GPU traffic
     of a train step.
 """
+import os
 from dataclasses import dataclass, field
 from typing import List, Sequence
 
@@ -50,6 +51,39 @@ def _distributed():
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
+class _EpochGraph:
+    """One PPO epoch's forward + loss + backward as a CUDA graph over static copies of the update's inputs.  The K epochs of an
+    update evaluate the same states with the same shapes (and so do the following updates of a training run), while the eager
+    epoch is ~1500 kernel launches of a few microseconds each: launch-bound.  Captured after one eager epoch of the same shapes;
+    the optimiser step and the gradient all-reduce stay outside (eager), so the graph holds no collective."""
+
+    def __init__(self, ppo, inputs):
+        self.static = [t.clone() for t in inputs]
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.critic_loss = ppo._epoch_forward_backward(*self._unflatten(self.static))
+
+    @staticmethod
+    def flatten(g1, g2, actions, logprobs, rewards):
+        return [g1.x, g1.adj, g1.mask, g1.num_nodes, g2.x, g2.adj, g2.mask, g2.num_nodes, actions, logprobs, rewards]
+
+    @staticmethod
+    def _unflatten(t):
+        return DenseGraphBatch(*t[0:4]), DenseGraphBatch(*t[4:8]), t[8], t[9], t[10]
+
+    @staticmethod
+    def signature(inputs):
+        return tuple((tuple(t.shape), t.dtype) for t in inputs)
+
+    def load(self, inputs):
+        for dst, src in zip(self.static, inputs):
+            dst.copy_(src)
+
+    def replay(self):
+        self.graph.replay()
+        return self.critic_loss
+
+
 class PPO:
     def __init__(self, args: PPOConfig, device):
         self.lr, self.betas, self.gamma, self.eps_clip, self.K_epochs = args.learning_rate, args.betas, args.gamma, args.eps_clip, args.k_epochs
@@ -71,12 +105,45 @@ class PPO:
         self.MseLoss = nn.MSELoss()
         # One flat gradient bucket, every p.grad a view into it: zeroing is one fill, the data-parallel reduction is one
         # NCCL call on the bucket itself (no gather / scatter copies of the 77 parameter gradients per epoch).
+        self.use_cuda_graph = os.environ.get("GED_B200_PPO_GRAPH", "1") != "0"
+        self._graphs = {}
         params = list(self.policy.parameters())
         self._flat_grad = torch.zeros(sum(p.numel() for p in params), device=device)
         o = 0
         for p in params:
             p.grad = self._flat_grad[o:o + p.numel()].view_as(p)
             o += p.numel()
+
+    def _epoch_forward_backward(self, old_graph_1, old_graph_2, old_actions, old_logprobs, rewards):
+        """Forward, clipped-surrogate + critic + entropy loss and backward of one epoch (ged_ppo_bihyb_train.py:192-214); the
+        gradients land in the flat bucket.  Returns the epoch's critic loss (detached)."""
+        logprobs, state_values, dist_entropy = self.policy.evaluate(old_graph_1, old_graph_2, old_actions)
+        ratios = torch.exp(logprobs - old_logprobs)
+        advantages = rewards - state_values.detach()
+        surr1 = ratios * advantages
+        surr2 = torch.clamp(ratios, 1 - self.eps_clip, 1 + self.eps_clip) * advantages
+        actor_loss = -torch.min(surr1, surr2)
+        critic_loss = self.MseLoss(state_values, rewards)
+        entropy_reg = -0.01 * dist_entropy
+        self._flat_grad.zero_()
+        (actor_loss + critic_loss + entropy_reg).mean().backward()      # accumulates in place into the bucket views
+        return critic_loss.detach().mean()
+
+    def _epoch_graph(self, inputs, capture: bool = False):
+        """The captured epoch for these input shapes, loaded with these inputs; None when there is none (yet)."""
+        if not self.use_cuda_graph or inputs[0].device.type != "cuda":
+            return None
+        sig = _EpochGraph.signature(inputs)
+        g = self._graphs.get(sig)
+        if g is None:
+            if not capture:
+                return None
+            if len(self._graphs) >= 4:               # a handful of shapes per run (the padded node count of the training batch)
+                self._graphs.pop(next(iter(self._graphs)))
+            g = self._graphs[sig] = _EpochGraph(self, inputs)
+            return g
+        g.load(inputs)
+        return g
 
     def _discounted_rewards(self, memory):
         with torch.no_grad():
@@ -127,18 +194,16 @@ class PPO:
         old_actions = torch.cat(memory.actions, dim=1).to(self.device)
         old_logprobs = torch.cat(memory.logprobs, dim=1).to(self.device).detach()
         critic_loss_sum = 0
-        for _ in range(self.K_epochs):
-            logprobs, state_values, dist_entropy = self.policy.evaluate(old_graph_1, old_graph_2, old_actions)
-            ratios = torch.exp(logprobs - old_logprobs)
-            advantages = rewards - state_values.detach()
-            surr1 = ratios * advantages
-            surr2 = torch.clamp(ratios, 1 - self.eps_clip, 1 + self.eps_clip) * advantages
-            actor_loss = -torch.min(surr1, surr2)
-            critic_loss = self.MseLoss(state_values, rewards)
-            entropy_reg = -0.01 * dist_entropy
-            critic_loss_sum = critic_loss_sum + critic_loss.detach().mean()
-            self._flat_grad.zero_()
-            (actor_loss + critic_loss + entropy_reg).mean().backward()      # accumulates in place into the bucket views
+        inputs = _EpochGraph.flatten(old_graph_1, old_graph_2, old_actions, old_logprobs, rewards)
+        graph = self._epoch_graph(inputs)            # None: eager (CPU, graphs switched off, or the first epoch of a new shape)
+        for epoch in range(self.K_epochs):
+            if graph is None and epoch == 1:         # one eager epoch of these shapes has run: capture the rest
+                graph = self._epoch_graph(inputs, capture=True)
+            if graph is not None:
+                critic_loss = graph.replay()
+            else:
+                critic_loss = self._epoch_forward_backward(old_graph_1, old_graph_2, old_actions, old_logprobs, rewards)
+            critic_loss_sum = critic_loss_sum + critic_loss
             if _distributed():          # equal shard sizes: the mean of the rank gradients is the global-batch gradient
                 dist.all_reduce(self._flat_grad)
                 self._flat_grad /= dist.get_world_size()

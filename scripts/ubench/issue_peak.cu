@@ -1,6 +1,6 @@
 // Measured instruction-issue roofs of one B200 (sm_100a) for the roofline of the GED solve kernel, which is bound by
 // instruction issue / the ALU pipe, not by HBM or tensor cores.
-// Whole-GPU kernels of independent instruction streams (8 chains per thread, 64 warps per SM), timed with CUDA events:
+// Whole-GPU kernels of independent instruction streams (8 chains per thread, 32 warps per SM), timed with CUDA events:
 //   fma   : FFMA only            -> issue limit of an SM sub-partition (1 warp instruction per clock)
 //   alu   : LOP3 only            -> the ALU pipe (integer / logic / select / compare: 16 lanes per sub-partition)
 //   fp64  : DADD only            -> the FP64 pipe
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(1024, 2) stream_kernel(float *out, const float
 template <int MODE>
 static double run(int sms, float *out, const float *in, long long *clk, int trips, double *sm_mhz)
 {
-    const int grid = sms * 2, block = 1024;
+    const int grid = sms, block = 1024;      // one CTA per SM: block 0's clock64 span is the kernel's (sm_mhz)
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
@@ -88,7 +88,7 @@ int main()
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     float *out, *in;
     long long *clk;
-    cudaMalloc(&out, sizeof(float) * sms * 2 * 1024);
+    cudaMalloc(&out, sizeof(float) * sms * 1024);
     cudaMalloc(&in, 64);
     cudaMalloc(&clk, 64);
     cudaMemset(in, 0, 64);

@@ -101,6 +101,32 @@ def test_device_rollout_equals_list_rollout(cuda_device):
     assert torch.equal(state.adj1, DeviceGEDState(env, g1, g2).adj1)                                   # the start state is left untouched
 
 
+def test_graph_captured_update_equals_eager_update(cuda_device, monkeypatch):
+    """PPO.update with the K epochs replayed from a CUDA graph (captured after the first eager epoch; a second update of the
+    same shapes reuses the graph with new inputs) leaves the parameters of the eager update."""
+    g1, g2 = _pairs(cuda_device, num=8, seed=905)
+    env = GEDenv("ipfp", "AIDS-20-30", device=cuda_device)
+    geds, _, _ = env.solve_feasible_ged_batch(g1, g2, "ipfp")
+    state = DeviceGEDState(env, g1, g2)
+    results = []
+    for graphs in ("1", "0"):
+        monkeypatch.setenv("GED_B200_PPO_GRAPH", graphs)
+        torch.manual_seed(0)
+        ppo = ppo_mod.PPO(ppo_mod.PPOConfig(update_timestep=3, k_epochs=4), cuda_device)
+        assert ppo.use_cuda_graph == (graphs == "1")
+        torch.manual_seed(13)
+        mem, t, losses = ppo_mod.Memory(), 0, []
+        for _ in range(2):                                   # two updates: capture in the first, pure replay in the second
+            t, _, loss = ppo_mod.rollout_episode_device(ppo, state, torch.cat(geds), mem, 3, t, 3)
+            losses += loss
+        assert len(ppo._graphs) == (1 if graphs == "1" else 0)
+        results.append(([p.detach().clone() for p in ppo.policy.parameters()], [float(x) for x in losses]))
+    (pa, la), (pb, lb) = results
+    assert np.allclose(la, lb, rtol=1e-5)
+    for a, b in zip(pa, pb):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)
+
+
 def test_device_beam_search_equals_list_beam_search(cuda_device):
     """The device-resident search and the Data-list search expand the same candidates and return the same best edit
     sequences (deterministic policy, both padded to the same node count)."""
