@@ -450,7 +450,7 @@ def main():
                        "note": "not the binding roof: ~1e3 executed instructions per compulsory byte"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / args.steps, "ms_steps_rank0": [round(ms, 2) for ms, _ in runs], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args, world), "l2": "flushed between steps (256 MiB write)",
                        "mean_ipfp_iterations": mean_iters, "mean_ged": mean_ged, "failed_solves": status_bad,
