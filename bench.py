@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Throughput of the GED lower-level solver hot path: IPFP pair-solves/sec at AIDS-50+ shape (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scaling strong --total 131072]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 A "step" = one pass of the hot path over one candidate batch: every candidate (base pair, edge edit) of the batch is
@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--pairs", type=int, default=64, help="base pairs per GPU")
     ap.add_argument("--edits", type=int, default=256, help="candidate edge edits per base pair")
     ap.add_argument("--max-iter", type=int, default=100)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the driver's contract): --pairs x --edits candidates PER GPU; strong: --total candidates over all GPUs")
+    ap.add_argument("--total", type=int, default=131072, help="--scaling strong: candidates of the whole job")
     ap.add_argument("--cpu-sample", type=int, default=0, help="candidates in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -54,14 +57,22 @@ def workload(args, rank, world=1):
     import numpy as np
     from ppo_bihyb_b200 import sharding, synthetic
     pairs = synthetic.make_pairs(args.config, args.pairs, seed_offset=100)
-    base, eu, ev = synthetic.make_edits(pairs, args.edits * world, seed_offset=100)
+    base, eu, ev = synthetic.make_edits(pairs, per_pair_edits(args, world), seed_offset=100)
     if world > 1:      # the list is grouped by base pair: interleaving gives every rank the same mix of pairs
         idx = sharding.shard_indices(len(base), rank, world, interleave=True)
         base, eu, ev = base[idx], eu[idx], ev[idx]
     return pairs, base, eu, ev
 
 
+def per_pair_edits(args, world):
+    """edge-edit candidates per base pair of the whole job: fixed per GPU (weak) or fixed in total (strong)"""
+    return args.edits * world if args.scaling == "weak" else max(1, args.total // args.pairs)
+
+
 def workload_name(args, world):
+    if args.scaling == "strong":
+        return (f"{args.config} synthetic pairs, {args.pairs} base pairs x {per_pair_edits(args, world)} edge-edit candidates in total "
+                f"({args.pairs * per_pair_edits(args, world)} candidate solves per step, interleaved over {world} GPU(s)), max_iter {args.max_iter}")
     return (f"{args.config} synthetic pairs, {args.pairs} base pairs x {args.edits} edge-edit candidates per GPU "
             f"({args.pairs * args.edits * world} candidate solves per step, interleaved over {world} GPU(s)), max_iter {args.max_iter}")
 
@@ -157,7 +168,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     line = {
         "impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "gpu_launches": 0,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "gpu_launches": 0,
     }
     port_value, port_dt, _, _ = cpu_port(args, args.cpu_sample or max(128, 8 * cores), cores)
     port = {"value": port_value, "unit": UNIT, "cores": cores, "kind": "port",
@@ -259,7 +270,7 @@ def issue_roofline(args, world, kernel_ms, lap_steps_per_step):
         prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_r02.json")))
     except (OSError, ValueError):
         pass
-    sig = f"{args.config}|{args.pairs}|{args.edits}|{args.max_iter}"
+    sig = f"{args.config}|{args.pairs}|{args.edits}|{args.max_iter}" if args.scaling == "weak" else f"strong|{args.config}|{args.pairs}|{args.total}|{world}"
     w = prof.get("workloads", {}).get(sig)
     roof = {"bound": "issue", "unit": "warp-instructions/s", "kernel": "ged_solve_kernel", "peak_source": src,
             "lap_scan_steps_per_s": lap_steps_per_step / (kernel_ms * 1e-3) if lap_steps_per_step else None,
@@ -319,7 +330,8 @@ def main():
 
     pairs, base, eu, ev = workload(args, rank, world)
     B = len(base)
-    B_max = -(-args.pairs * args.edits * world // world)                 # shards differ by at most one candidate
+    total_candidates = args.pairs * per_pair_edits(args, world)
+    B_max = -(-total_candidates // world)                                # shards differ by at most one candidate
     ps = PairSet.from_host(pairs, dev)
     base_d = torch.from_numpy(base).to(dev)
     eu_d, ev_d = torch.from_numpy(eu).to(dev), torch.from_numpy(ev).to(dev)
@@ -430,7 +442,6 @@ def main():
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_total, e2e_total = float(tmax[0]), float(tmax[1])
-    total_candidates = args.pairs * args.edits * world
 
     if rank == 0:
         value = total_candidates * args.steps / (ms_total * 1e-3)
@@ -450,7 +461,7 @@ def main():
                        "note": "not the binding roof: ~1e3 executed instructions per compulsory byte"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_total / args.steps, "ms_steps_rank0": [round(ms, 2) for ms, _ in runs], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / args.steps, "ms_steps_rank0": [round(ms, 2) for ms, _ in runs], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args, world), "l2": "flushed between steps (256 MiB write)",
                        "mean_ipfp_iterations": mean_iters, "mean_ged": mean_ged, "failed_solves": status_bad,

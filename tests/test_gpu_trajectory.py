@@ -18,8 +18,9 @@ from test_oracle_trajectory import REL, SHAPES, records_of
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("hint", [0, 2], ids=["one-warp-per-candidate", "one-cta-per-candidate"])
 @pytest.mark.parametrize("name", SHAPES)
-def test_kernels_teacher_forced_along_the_reference_trajectory(cuda_device, name):
+def test_kernels_teacher_forced_along_the_reference_trajectory(cuda_device, name, hint):
     z = load("trajectory_" + name)
     pairs = pairs_of(z)
     recs = list(records_of(z))
@@ -43,7 +44,7 @@ def test_kernels_teacher_forced_along_the_reference_trajectory(cuda_device, name
 
     # (2) one IPFP iteration from the reference's iterate (ged_solve_desc.x_init): K v within 1e-5 relative of the reference's
     #     mm, identical bits to the oracle's replay, ub exact, next iterate within 1e-5
-    res = solver.solve_batch(ps, base_idx=base, x_init=X.to(cuda_device), max_iter=1, trace=True, check=True)
+    res = solver.solve_batch(ps, base_idx=base, x_init=X.to(cuda_device), max_iter=1, trace=True, check=True, launch_hint=hint)
     tr = {k: t.cpu().numpy() for k, t in res.trace.items()}
     worst_cost = worst_x = 0.0
     flipped = 0
