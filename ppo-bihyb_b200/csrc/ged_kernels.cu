@@ -2357,6 +2357,7 @@ int launch_solve(const SolveParams &prm, cudaStream_t stream)
 }
 
 // ---- team (CTA-per-candidate) launches: their own translation unit (-DGED_TU_TEAM) --------------------------------------
+constexpr int kTeamDoesNotFit = -1;          // not an error: the pair's team CTA exceeds shared memory
 int launch_solve_team(int W, const SolveParams &prm, cudaStream_t stream);
 
 #ifdef GED_TU_TEAM
@@ -2364,7 +2365,7 @@ template <int W>
 int launch_team(SolveParams prm, cudaStream_t stream)
 {
     const int smem = team_smem_bytes(prm.layout, W, prm.pairs.max_n2);
-    if (smem > kMaxSmemBytes) return fail(GED_E_TOO_LARGE, "pair too large for a team CTA's shared memory");
+    if (smem > kMaxSmemBytes) return kTeamDoesNotFit;          // the caller falls back to the one-warp launch
     cudaError_t e = cudaFuncSetAttribute(ged_solve_team_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail_cuda(e, "ged_solve_batch (team)");
     int dev = 0, sms = 0;
@@ -2529,7 +2530,10 @@ int ged_solve_batch(const ged_solve_desc *d, const ged_solve_out *o, void *strea
     const int S = slots_for(d->pairs.max_n1, d->pairs.max_n2);
     // launch_hint 2: a latency-bound call -- the W = S warps of a CTA share one candidate (team kernel); pairs of up to 32
     // nodes (one slot per lane already) and builds without it take the spread launch.
-    if (d->launch_hint == 2 && S >= 2 && S <= kTeamMaxW && env_int("GED_B200_TEAM", 1)) return launch_solve_team(S, prm, (cudaStream_t)stream);
+    if (d->launch_hint == 2 && S >= 2 && S <= kTeamMaxW && env_int("GED_B200_TEAM", 1)) {
+        const int rc = launch_solve_team(S, prm, (cudaStream_t)stream);
+        if (rc != kTeamDoesNotFit) return rc;
+    }
     return dispatch_solve(S, prm, (cudaStream_t)stream);
 }
 

@@ -115,3 +115,26 @@ def test_team_status_bits(cuda_device):
     b = solver.solve_batch(ps, launch_hint=PACKED)
     assert torch.equal(a.status, b.status) and int(a.status[1]) != 0 and int(a.status[0]) == 0
     assert torch.equal(a.ged[[0, 2]], b.ged[[0, 2]])
+
+
+def test_team_explicit_node_costs_and_the_largest_pairs(cuda_device):
+    """An explicit fp32 node-cost matrix (the route of the non-AIDS ``node_metric`` tables, ged_env.py:235-242) through the team
+    launch, and pairs at the size limit (224 nodes), whose team CTA may not fit shared memory -- the call then takes the one-warp
+    launch instead of failing."""
+    rng = np.random.default_rng(7)
+    pairs = synthetic.make_pairs("aids-30-50", 4, seed_offset=47)
+    costs = []
+    for g1, g2 in pairs:
+        c = rng.integers(0, 4, (g1.n + 1, g2.n + 1)).astype(np.float32) / 2.0
+        c[g1.n, g2.n] = 0.0
+        costs.append(c)
+    ps = PairSet.from_host(pairs, cuda_device, node_costs=costs)
+    a = solver.solve_batch(ps, check=True, trace=True, max_iter=12, launch_hint=TEAM)
+    b = solver.solve_batch(ps, check=True, trace=True, max_iter=12, launch_hint=PACKED)
+    _same(a, b, trace=True)
+    g1, g2 = pairs[0]
+    o = go.solve(g1.adj, g2.adj, costs[0], max_iter=12)
+    assert float(a.ged[0]) == o["ged"] and int(a.iters[0]) == o["iters"]
+    big = synthetic.make_pairs("n=224", 1, seed_offset=49)
+    psb = PairSet.from_host(big, cuda_device)
+    _same(solver.solve_batch(psb, check=True, max_iter=2, launch_hint=TEAM), solver.solve_batch(psb, check=True, max_iter=2, launch_hint=PACKED))
