@@ -18,6 +18,8 @@ ap.add_argument("--config", default="aids-50+")
 ap.add_argument("--pairs", type=int, default=64)
 ap.add_argument("--edits", type=int, default=256)
 ap.add_argument("--max-iter", type=int, default=100)
+ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+ap.add_argument("--total", type=int, default=131072)
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 pairs, base, eu, ev = bench.workload(args, 0)
