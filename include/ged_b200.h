@@ -109,7 +109,8 @@ typedef struct ged_solve_desc {
      * whose candidates are each solved by ALL warps of a CTA (one warp per 32 columns of the LAP, rows of K.X dealt out to the
      * warps): the reference's per-step fan-out (<= 27 candidates per pair, ged_ppo_bihyb_eval.py:95-100; batch_size solves
      * per rollout step, ged_ppo_bihyb_train.py:294-298) then finishes in 1/2 to 2/3 of a one-warp solve's time; pairs of up
-     * to 32 nodes are launched as with hint 1.  Results are bit-identical under every hint. */
+     * to 32 nodes keep a one-warp LAP with three helper warps for K.X and the update (1.15x; calls of <= 512 candidates).
+     * Results are bit-identical under every hint. */
     int32_t launch_hint;
 } ged_solve_desc;
 

@@ -1561,11 +1561,11 @@ __device__ __forceinline__ float team_cost_at(const float *cost, const Slice &sm
 }
 
 // kv_apply by the W warps of a CTA: rows dealt out round robin; results and every rounding identical to kv_apply.
-template <int W>
-__device__ void kv_team(const Pair &P, const Slice &sm, float *rowbuf, const float *X, float *Y, const SmemCost<W> &store,
+template <int S, int W>
+__device__ void kv_team(const Pair &P, const Slice &sm, float *rowbuf, const float *X, float *Y, const SmemCost<S> &store,
                         float *trace, TeamXch *xch, double &s_vv_out, bool &invalid_out)
 {
-    constexpr int T = W + 1;
+    constexpr int T = S + 1;                                   // 32-column tiles of a row; W = warps of the CTA
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int R = P.R, C = P.C, n1 = P.n1, n2 = P.n2;
     const bool fast = P.maxdeg <= kMaxDeg;
@@ -1695,7 +1695,7 @@ __device__ void kv_team(const Pair &P, const Slice &sm, float *rowbuf, const flo
             sres = __fsub_rn(sres, __fadd_rn(T3, T3));
             const float d = in_row ? __fmul_rn(node_cost_at(P, sm, i, a), xia) : 0.0f;
             const float c = __fadd_rn(sres, d);
-            emit_cost<W>(store, sm, n1, n2, i, t, c);
+            emit_cost<S>(store, sm, n1, n2, i, t, c);
             if (in_row) {
                 if (!(i == n1 && a == n2)) bad |= (c != c) || (c == -INFINITY);
                 if (trace) trace[i * C + a] = c;
@@ -1718,14 +1718,33 @@ __device__ void kv_team(const Pair &P, const Slice &sm, float *rowbuf, const flo
     s_vv_out = warp_butterfly(svv);
 }
 
-// One candidate solve by the W warps of a CTA (solve_one for a team).
-template <int W>
+// One candidate solve by the W warps of a CTA (solve_one for a team).  S = 32-column slots of the pair: S == W is the team
+// proper (LAP columns dealt out to the warps); S == 1 < W serves pairs of up to 32 nodes, whose LAP has nothing to deal out --
+// warp 0 runs the one-warp LAP (lsape_warp<1>) while the K.X passes, the line-search update and the set-up (19-24 % of a lone
+// warp's solve at n = 25) are still split over the W warps.
+template <int W, int S>
+__device__ int team_lsape(const SmemCost<S> &store, bool invalid, int n1, int n2, const Slice &sm, TeamXch *xch, int &xp,
+                          unsigned long long *steps)
+{
+    if constexpr (S == W) return lsape_team<W>(store.base, invalid, n1, n2, sm, xch, xp, steps);
+    else {
+        if (threadIdx.x < 32) {
+            const int st = lsape_warp<S>(store, invalid, n1, n2, sm, steps);
+            if (threadIdx.x == 0) xch->status = st;
+        }
+        __syncthreads();
+        return xch->status;
+    }
+}
+
+template <int W, int S>
 __device__ void solve_team(const SolveParams &prm, int b, const Slice &sm, float *rowbuf, TeamXch *xch, int &xp)
 {
+    static_assert(S == W || S == 1, "team shapes: one warp per 32-column slot, or helpers around a one-slot LAP");
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nthr = 32 * W;
     const ged_solve_out &out = prm.out;
     const int p = prm.base_idx ? prm.base_idx[b] : b;
-    const SmemCost<W> store{sm.cost, prm.pairs.n2[p]};
+    const SmemCost<S> store{sm.cost, prm.pairs.n2[p]};
     Pair P;
     if (threadIdx.x == 0) xch->status = 0;
     __syncthreads();
@@ -1794,9 +1813,9 @@ __device__ void solve_team(const SolveParams &prm, int b, const Slice &sm, float
             __syncthreads();
         } else {
             // hungarian_ged (ged_env.py:303-326): v0 = LSAPE(node_cost_mat); the closed form is cheap: warp 0 alone
-            if (w == 0) init_cost_closed_form<W>(P, sm, store, out.tr_init_cost ? out.tr_init_cost + (long long)b * prm.mat_stride : nullptr);
+            if (w == 0) init_cost_closed_form<S>(P, sm, store, out.tr_init_cost ? out.tr_init_cost + (long long)b * prm.mat_stride : nullptr);
             __syncthreads();
-            status |= lsape_team<W>(store.base, false, n1, n2, sm, xch, xp, &lap_steps);
+            status |= team_lsape<W, S>(store, false, n1, n2, sm, xch, xp, &lap_steps);
             if (status == 0) {
                 for (int i = threadIdx.x; i < n1; i += nthr) {
                     sm.bestrow[i] = sm.rowmatch[i];
@@ -1819,15 +1838,15 @@ __device__ void solve_team(const SolveParams &prm, int b, const Slice &sm, float
             iters = it + 1;
             double s_vv;
             bool invalid;
-            kv_team<W>(P, sm, rowbuf, X, Y, store, out.tr_cost ? out.tr_cost + ((long long)b * prm.max_iter + it) * prm.mat_stride : nullptr,
+            kv_team<S, W>(P, sm, rowbuf, X, Y, store, out.tr_cost ? out.tr_cost + ((long long)b * prm.max_iter + it) * prm.mat_stride : nullptr,
                        xch, s_vv, invalid);                                                    // ged_env.py:269
-            status |= lsape_team<W>(store.base, invalid, n1, n2, sm, xch, xp, &lap_steps);      // :270
+            status |= team_lsape<W, S>(store, invalid, n1, n2, sm, xch, xp, &lap_steps);      // :270
             if (status != 0) break;
             // scalars: functions of shared data only -> every warp computes them, control flow stays uniform
             const double ub = score_assignment(P, sm, nnz1, nnz2, sm.rowmatch, sm.colmatch);   // :271
             const bool better = ub < best_ub;                                                 // :272-274
             if (better) best_ub = ub;
-            const double s_vb = matched_cost_sum<W>(store, sm, n1, n2);
+            const double s_vb = matched_cost_sum<S>(store, sm, n1, n2);
             const double alpha = __dsub_rn(s_vb, s_vv);                                        // :275
             const double beta = __dadd_rn(__dsub_rn(ub, __dadd_rn(s_vb, s_vb)), s_vv);         // :277
             const double t0 = __ddiv_rn(-alpha, beta);                                         // :278
@@ -1923,7 +1942,7 @@ __host__ __device__ inline int team_smem_bytes(const SliceLayout &L, int W, int 
     return L.bytes + L.cost_bytes + W * team_rowbuf_bytes(max_n2) + (int)sizeof(TeamXch);
 }
 
-template <int W>
+template <int W, int S>
 __global__ void __launch_bounds__(32 * W) ged_solve_team_kernel(SolveParams prm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1943,7 +1962,7 @@ __global__ void __launch_bounds__(32 * W) ged_solve_team_kernel(SolveParams prm)
         }
         if (slot >= prm.count) break;
         const int b = prm.order ? prm.order[slot] : slot;
-        solve_team<W>(prm, b, sm, rowbuf, xch, xp);
+        solve_team<W, S>(prm, b, sm, rowbuf, xch, xp);
     }
 }
 
@@ -2358,15 +2377,16 @@ int launch_solve(const SolveParams &prm, cudaStream_t stream)
 
 // ---- team (CTA-per-candidate) launches: their own translation unit (-DGED_TU_TEAM) --------------------------------------
 constexpr int kTeamDoesNotFit = -1;          // not an error: the pair's team CTA exceeds shared memory
+constexpr int kTeamHelpers = 4;              // warps of a team CTA around a one-slot (<= 32 nodes) pair
 int launch_solve_team(int W, const SolveParams &prm, cudaStream_t stream);
 
 #ifdef GED_TU_TEAM
-template <int W>
+template <int W, int S = W>
 int launch_team(SolveParams prm, cudaStream_t stream)
 {
     const int smem = team_smem_bytes(prm.layout, W, prm.pairs.max_n2);
     if (smem > kMaxSmemBytes) return kTeamDoesNotFit;          // the caller falls back to the one-warp launch
-    cudaError_t e = cudaFuncSetAttribute(ged_solve_team_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(ged_solve_team_kernel<W, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail_cuda(e, "ged_solve_batch (team)");
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
@@ -2380,18 +2400,18 @@ int launch_team(SolveParams prm, cudaStream_t stream)
         const int per_sm_needed = (prm.B + sms - 1) / sms;
         const int dflt = per_sm_needed * (smem + 1024) <= kSmemPerSm / 2 ? 50 : 100;
         const int carve = env_int("GED_B200_TEAM_CARVEOUT", dflt);
-        e = cudaFuncSetAttribute(ged_solve_team_kernel<W>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        e = cudaFuncSetAttribute(ged_solve_team_kernel<W, S>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (e != cudaSuccess) return fail_cuda(e, "ged_solve_batch (team)");
     }
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ged_solve_team_kernel<W>, 32 * W, smem) != cudaSuccess || per_sm < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ged_solve_team_kernel<W, S>, 32 * W, smem) != cudaSuccess || per_sm < 1)
         return fail(GED_E_CUDA, "ged_solve_batch (team): occupancy query failed");
     int grid = prm.count < sms * per_sm ? prm.count : sms * per_sm;      // persistent CTAs beyond one wave
     if (prm.ws_slots > 0 && grid > prm.ws_slots) grid = prm.ws_slots;    // one scratch row per CTA in flight
     if (env_int("GED_B200_VERBOSE", 0))
-        fprintf(stderr, "[ged_b200] team solve<W=%d> count=%d max_n=(%d,%d) grid=%d (%d CTAs/SM), %d B dynamic smem\n", W, prm.count,
+        fprintf(stderr, "[ged_b200] team solve<W=%d,S=%d> count=%d max_n=(%d,%d) grid=%d (%d CTAs/SM), %d B dynamic smem\n", W, S, prm.count,
                 prm.pairs.max_n1, prm.pairs.max_n2, grid, per_sm, smem);
-    ged_solve_team_kernel<W><<<grid, 32 * W, smem, stream>>>(prm);
+    ged_solve_team_kernel<W, S><<<grid, 32 * W, smem, stream>>>(prm);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(e, "ged_solve_batch (team)");
     return GED_OK;
@@ -2400,13 +2420,14 @@ int launch_team(SolveParams prm, cudaStream_t stream)
 int launch_solve_team(int W, const SolveParams &prm, cudaStream_t stream)
 {
     switch (W) {
+    case 1: return launch_team<kTeamHelpers, 1>(prm, stream);       // pairs of up to 32 nodes: one-warp LAP, the rest split
     case 2: return launch_team<2>(prm, stream);
     case 3: return launch_team<3>(prm, stream);
     case 4: return launch_team<4>(prm, stream);
     case 5: return launch_team<5>(prm, stream);
     case 6: return launch_team<6>(prm, stream);
     case 7: return launch_team<7>(prm, stream);
-    default: return fail(GED_E_BADARG, "team launch: 2..7 warps");
+    default: return fail(GED_E_BADARG, "team launch: 1..7 slots");
     }
 }
 #endif  // GED_TU_TEAM
@@ -2528,9 +2549,10 @@ int ged_solve_batch(const ged_solve_desc *d, const ged_solve_out *o, void *strea
     prm.out = *o;
     prm.layout = make_layout(d->pairs.max_n1, d->pairs.max_n2);
     const int S = slots_for(d->pairs.max_n1, d->pairs.max_n2);
-    // launch_hint 2: a latency-bound call -- the W = S warps of a CTA share one candidate (team kernel); pairs of up to 32
-    // nodes (one slot per lane already) and builds without it take the spread launch.
-    if (d->launch_hint == 2 && S >= 2 && S <= kTeamMaxW && env_int("GED_B200_TEAM", 1)) {
+    // launch_hint 2: a latency-bound call -- the warps of a CTA share one candidate (team kernel).
+    // (pairs of up to 32 nodes: one-warp LAP with three helper warps for everything else -- 1.15x at <= 300 candidates, a loss at 1024:
+    //  up to GED_B200_TEAM_S1_MAX candidates only)
+    if (d->launch_hint == 2 && S <= kTeamMaxW && env_int("GED_B200_TEAM", 1) && (S >= 2 || d->B <= env_int("GED_B200_TEAM_S1_MAX", 512))) {
         const int rc = launch_solve_team(S, prm, (cudaStream_t)stream);
         if (rc != kTeamDoesNotFit) return rc;
     }

@@ -1,7 +1,8 @@
 """GPU: the CTA-per-candidate ("team") launches (ged_solve_desc.launch_hint = 2, csrc/ged_kernels.cu: ged_solve_team_kernel) --
 all warps of a CTA share one candidate: LAP columns dealt out to the warps, rows of K.X dealt out to the warps.  They must
 return the bits of the one-warp kernels and of the oracle: whole trajectories, every launch path (edits, scoring graph,
-teacher forcing, Hungarian only, more candidates than one wave), every team width W = 2..7."""
+teacher forcing, Hungarian only, more candidates than one wave), every team width W = 2..7, and the helper-warp shape of pairs
+of up to 32 nodes (one-warp LAP, K.X and update split over four warps)."""
 import numpy as np
 import pytest
 import torch
@@ -25,7 +26,7 @@ def _same(a, b, trace=False):
             assert torch.equal(x, y) or bool(((x == y) | (x.isnan() & y.isnan())).all()), k
 
 
-@pytest.mark.parametrize("config,num", [("aids-30-50", 6), ("aids-50+", 5), ("n=100", 2)])
+@pytest.mark.parametrize("config,num", [("aids-20-30", 8), ("aids-30-50", 6), ("aids-50+", 5), ("n=100", 2)])
 def test_team_trajectory_equals_one_warp_kernel_and_oracle(cuda_device, config, num):
     """Whole trajectories (Hungarian start, every iteration's cost matrix, projection, six scalars, iterate, iteration and
     LAP scan-step counts, result): team == one warp per candidate, and == the oracle on the first pairs."""
@@ -70,6 +71,11 @@ def test_team_candidate_edits_size_classes_and_persistent_ctas(cuda_device):
     team = solver.solve_batch(ps, launch_hint=TEAM, **kw)
     _same(team, solver.solve_batch(ps, launch_hint=PACKED, **kw))
     _same(team, solver.solve_batch(ps, **kw))                       # whatever the size-based default picks
+    pairs = synthetic.make_pairs("aids-20-30", 10, seed_offset=30)
+    edits = synthetic.make_edits(pairs, 27, seed_offset=30)
+    ps = PairSet.from_host(pairs, cuda_device)
+    kw = dict(base_idx=edits[0], edit_u=edits[1], edit_v=edits[2], check=True)
+    _same(solver.solve_batch(ps, launch_hint=TEAM, **kw), solver.solve_batch(ps, launch_hint=PACKED, **kw))
     pairs = synthetic.make_pairs("aids-30-50", 12, seed_offset=31)
     edits = synthetic.make_edits(pairs, 120, seed_offset=31)        # 1440 candidates
     ps = PairSet.from_host(pairs, cuda_device)
