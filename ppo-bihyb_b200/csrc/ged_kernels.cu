@@ -1706,13 +1706,24 @@ __device__ void kv_team(const Pair &P, const Slice &sm, float *rowbuf, const flo
     __syncthreads();                                           // cost matrix complete
     invalid_out = xch->bad != 0;
     // s_vv = <cost, X> in the canonical order (per lane: rows ascending, tiles ascending; fp64), by every warp
+    // (the row of X for step i + 1 is requested before row i is consumed: X is global, one L2 round trip per row otherwise)
     double svv = 0.0;
+    float xn[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) { const int a = lane + 32 * t; xn[t] = (a < C) ? X[a] : 0.0f; }
     for (int i = 0; i < R; ++i) {
+        float xc[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            xc[t] = xn[t];
+            const int a = lane + 32 * t;
+            xn[t] = (i + 1 < R && a < C) ? X[(i + 1) * C + a] : 0.0f;
+        }
 #pragma unroll
         for (int t = 0; t < T; ++t) {
             if (32 * t >= C) break;
             const int a = lane + 32 * t;
-            if (a < C) svv = __dadd_rn(svv, __dmul_rn((double)team_cost_at(store.base, sm, n1, n2, i, a), (double)X[i * C + a]));
+            if (a < C) svv = __dadd_rn(svv, __dmul_rn((double)team_cost_at(store.base, sm, n1, n2, i, a), (double)xc[t]));
         }
     }
     s_vv_out = warp_butterfly(svv);
