@@ -4,7 +4,8 @@
 // [construct_k :160-228, never materialised] -> ipfp_ged :256-289 -> hungarian_ged :303-326 ->
 // hungarian_lap :329-351 -> scipy linear_sum_assignment :407 -> comp_ged :245-253.
 //
-// Execution model: ONE WARP PER CANDIDATE SOLVE.  The sequential core of the path is the LAP projection (a shortest-
+// Execution model of the throughput launches: ONE WARP PER CANDIDATE SOLVE (latency-bound calls of a few hundred candidates
+// take the CTA-per-candidate kernels further down: ged_solve_team_kernel).  The sequential core of the path is the LAP projection (a shortest-
 // augmenting-path search whose scan order and tie-breaks must equal SciPy's: ~2000 dependent scan steps per LAP at n=60,
 // 101 LAPs per solve), so a candidate is owned by a single warp that keeps the LAP's per-column state (dual v, shortest-
 // path cost, position in SciPy's `remaining` vector, predecessor) in REGISTERS, one column per (lane, slot).  Throughput
@@ -19,7 +20,8 @@
 // K is never built: K vec(X) is evaluated from the two bit-packed adjacency factors.  Warps never synchronise with each
 // other (the only CTA-wide barriers bracket the TMEM allocation).
 // Launches are persistent (as many CTAs as the device holds, warps pulling candidates from an atomic work queue) or, for
-// latency-bound calls of a few hundred candidates, spread one candidate per CTA (ged_solve_desc.launch_hint).
+// latency-bound calls of a few hundred candidates, spread one candidate per CTA or solved by all warps of a CTA
+// (ged_solve_desc.launch_hint 1 / 2).
 //
 // All floating-point arithmetic follows the canonical order documented in oracle/ged_oracle.c (no FMA contraction:
 // explicit *_rn intrinsics, and the file is compiled with --fmad=false).

@@ -15,6 +15,7 @@ SOLVERS = {"ipfp": _lib.GED_SOLVER_IPFP, "hungarian": _lib.GED_SOLVER_HUNGARIAN}
 
 
 # calls of at most this many candidates in total are latency-bound (a rollout / beam-search step): one candidate per CTA
+# (only reached when TEAM_MAX_CANDIDATES is set below it)
 SPREAD_MAX_CANDIDATES = 512
 # ... and of at most this many are solved by one CTA each (all warps of the CTA share the candidate: launch_hint 2)
 TEAM_MAX_CANDIDATES = int(os.environ.get("GED_B200_TEAM_MAX", "1024"))
