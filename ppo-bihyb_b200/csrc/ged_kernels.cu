@@ -362,9 +362,10 @@ __device__ __forceinline__ double double_from_ord(unsigned ohi, unsigned olo)
 #define GED_LAP_SHORTCUT 1
 #endif
 
-// if (live & MASK) && r < spc:  spc = r, pth = i, and below = 1 if also r < minVal
+// if (live & MASK) && r < spc:  spc = r, pth = i, and keep = 0 if also r < minVal.  `keep` starts a scan step as ~0 and is the
+// start value of the lane's tie-break bid (a minimum of keys), so a lane that wrote a value below minVal bids key 0 for free.
 template <unsigned MASK>
-__device__ __forceinline__ void lap_relax_below(double &spc, int &pth, int &below, double r, int i, unsigned live, double minVal)
+__device__ __forceinline__ void lap_relax_below(double &spc, int &pth, unsigned &keep, double r, int i, unsigned live, double minVal)
 {
     asm("{\n\t.reg .pred q, p, p2;\n\t.reg .b32 t;\n\t"
         "and.b32 t, %5, %6;\n\t"
@@ -373,8 +374,27 @@ __device__ __forceinline__ void lap_relax_below(double &spc, int &pth, int &belo
         "selp.f64 %0, %3, %0, p;\n\t"
         "selp.b32 %1, %4, %1, p;\n\t"
         "setp.lt.and.f64 p2, %3, %7, p;\n\t"
-        "@p2 mov.b32 %2, 1;\n\t}"
-        : "+d"(spc), "+r"(pth), "+r"(below) : "d"(r), "r"(i), "r"(live), "n"(MASK), "d"(minVal));
+        "@p2 mov.b32 %2, 0;\n\t}"
+        : "+d"(spc), "+r"(pth), "+r"(keep) : "d"(r), "r"(i), "r"(live), "n"(MASK), "d"(minVal));
+}
+
+// the same for the one entry of a row that is not part of a block (a real row's deletion entry, an insertion row's own
+// column): the slot is relaxed only in the lane and slot that own column k of the group, id = the column of the group this
+// lane's slot holds -- one integer compare chained into the predicate instead of a lane / slot mask built per step
+template <unsigned MASK>
+__device__ __forceinline__ void lap_relax_own_below(double &spc, int &pth, unsigned &keep, double r, int i, unsigned live, double minVal,
+                                                    int k, int id)
+{
+    asm("{\n\t.reg .pred q, p, p2;\n\t.reg .b32 t;\n\t"
+        "and.b32 t, %5, %6;\n\t"
+        "setp.ne.u32 q, t, 0;\n\t"
+        "setp.eq.and.s32 q, %8, %9, q;\n\t"
+        "setp.lt.and.f64 p, %3, %0, q;\n\t"
+        "selp.f64 %0, %3, %0, p;\n\t"
+        "selp.b32 %1, %4, %1, p;\n\t"
+        "setp.lt.and.f64 p2, %3, %7, p;\n\t"
+        "@p2 mov.b32 %2, 0;\n\t}"
+        : "+d"(spc), "+r"(pth), "+r"(keep) : "d"(r), "r"(i), "r"(live), "n"(MASK), "d"(minVal), "r"(k), "r"(id));
 }
 
 // if (live & MASK) && r < spc:  spc = r, pth = i (and, when TRACK, improved = 1)
@@ -424,6 +444,18 @@ __device__ __forceinline__ void lap_min_key(unsigned &lk, double spc, double min
         : "+r"(lk) : "d"(spc), "d"(minVal), "r"(live), "n"(MASK), "r"(posk), "r"(kx));
 }
 
+// position field of the winning key back as pos << 19:  (key ^ ~(key >>s 31)) & mask  (kk = pos for an assigned column,
+// bit 31 set; pos ^ 511 for an unassigned one)
+__device__ __forceinline__ int lap_winner_pos(unsigned mk, unsigned mask)
+{
+    int r;
+    asm("{\n\t.reg .b32 t;\n\t"
+        "shr.s32 t, %1, 31;\n\t"
+        "lop3.b32 %0, %1, t, %2, 0x82;\n\t}"
+        : "=r"(r) : "r"(mk), "r"(mask));
+    return r;
+}
+
 template <int S, int I = 0>
 struct LapSlots {
     // slots [LO, HI): relax with r = base - v[slot]
@@ -460,7 +492,7 @@ struct LapSlots {
     }
     // the same three with the `below` flag of the scan-step shortcut (see lap_relax_below)
     template <int LO, int HI>
-    static __device__ __forceinline__ void relax_base_below(double (&spc)[2 * S], int (&pth)[2 * S], int &below,
+    static __device__ __forceinline__ void relax_base_below(double (&spc)[2 * S], int (&pth)[2 * S], unsigned &below,
                                                             const double (&v)[2 * S], double base, int i, unsigned live, double minVal)
     {
         if constexpr (I < 2 * S) {
@@ -470,13 +502,25 @@ struct LapSlots {
         }
     }
     template <int LO, int HI>
-    static __device__ __forceinline__ void relax_one_below(double (&spc)[2 * S], int (&pth)[2 * S], int &below,
+    static __device__ __forceinline__ void relax_one_below(double (&spc)[2 * S], int (&pth)[2 * S], unsigned &below,
                                                            const double (&v)[2 * S], double base, int i, unsigned live_lane, int sel,
                                                            double minVal)
     {
         relax_base_below<LO, HI>(spc, pth, below, v, base, i, live_lane & ((1u << LO) << sel), minVal);
     }
-    static __device__ __forceinline__ void relax_row_below(double (&spc)[2 * S], int (&pth)[2 * S], int &below,
+    // slots [LO, HI) hold columns lane, lane + 32, ... of one group: relax the one that is column k of the group
+    template <int LO, int HI>
+    static __device__ __forceinline__ void relax_own_below(double (&spc)[2 * S], int (&pth)[2 * S], unsigned &below,
+                                                           const double (&v)[2 * S], double base, int i, unsigned live, int k, int lane,
+                                                           double minVal)
+    {
+        if constexpr (I < 2 * S) {
+            if constexpr (I >= LO && I < HI)
+                lap_relax_own_below<(1u << I)>(spc[I], pth[I], below, __dsub_rn(base, v[I]), i, live, minVal, k, lane + 32 * (I - LO));
+            LapSlots<S, I + 1>::template relax_own_below<LO, HI>(spc, pth, below, v, base, i, live, k, lane, minVal);
+        }
+    }
+    static __device__ __forceinline__ void relax_row_below(double (&spc)[2 * S], int (&pth)[2 * S], unsigned &below,
                                                            const double (&v)[2 * S], const float (&cs)[S], double minVal, double ui,
                                                            int i, unsigned live)
     {
@@ -519,9 +563,15 @@ struct LapSlots {
 // The expanded matrix is never formed: its real block comes from the cost store, row i's deletion entry from
 // sm.cdel[i], column a's insertion entry from sm.cdel[n1 + a], everything else is +inf or 0 by construction.
 // Columns live in registers, one per (lane, slot): real column a -> lane a & 31, slot a >> 5; deletion column n2+k ->
-// lane k & 31, slot S + (k >> 5).  Tie-break key of a column:  kk << 18 | slot << 14 | lane << 9 | (row4col + 1), with
-// kk = pos ^ 511 for an unassigned column (SciPy: the LAST unassigned minimum wins) and pos ^ 512 = 512 + pos for an
-// assigned one (else the FIRST minimum wins); pos = index in SciPy's `remaining` vector.  The smallest key wins.
+// lane k & 31, slot S + (k >> 5).  Tie-break key of a column (the smallest key wins):
+//     assigned << 31 | kk << 19 | lane << 14 | slot << 9 | row
+// with pos = the column's index in SciPy's `remaining` vector, kk = pos ^ 511 for an unassigned column (SciPy: the LAST
+// unassigned minimum wins) and kk = pos for an assigned one (else the FIRST minimum wins; bit 31 puts every assigned column
+// behind every unassigned one), row = row4col of an assigned column and the sentinel N -- a valid index of the padded u / cdel
+// arrays -- for an unassigned one.  The layout is chosen for the bookkeeping after the reduction: the next row is key & 511
+// without a decrement or a clamp, the slot field is five bits wide so that a wrapping shift takes 1 << slot straight from
+// key >> 9, and the winner's position is (key ^ ~(key >>s 31)) & 511 << 19.  pos is unique per column, so the bits below kk
+// never decide a comparison.
 // `invalid` = the producer of the matrix saw NaN / -inf (scipy: RECTANGULAR_LSAP_INVALID).
 // ---------------------------------------------------------------------------------------------------------------
 template <int S, class Store>
@@ -544,6 +594,8 @@ __device__ int lsape_warp(const Store &store, bool invalid, int n1, int n2, cons
     for (int t = lane; t < N; t += 32) { u[t] = 0.0; sm.row4col[t] = -1; sm.col4row[t] = -1; }
     __syncwarp();
 
+    constexpr unsigned kPosShift = 19, kPosMask = 511u << kPosShift;
+    const unsigned one = 1u;
     unsigned long long steps = 0;
     for (int cur = 0; cur < N; ++cur) {
         double spc[2 * S];
@@ -553,17 +605,16 @@ __device__ int lsape_warp(const Store &store, bool invalid, int n1, int n2, cons
             const int j = (s < S) ? (lane + 32 * s) : (n2 + lane + 32 * (s - S));
             spc[s] = INFINITY;
             pth[s] = -1;
-            posk[s] = (N - 1 - j) << 18;
+            posk[s] = (N - 1 - j) << kPosShift;
             int r4 = -1;
             if ((exist >> s) & 1u) r4 = sm.row4col[j];
-            kx[s] = (((r4 >= 0) ? 512 : 511) << 18) | (s << 14) | (lane << 9) | (r4 + 1);
+            kx[s] = (int)(((r4 >= 0) ? 0x80000000u : kPosMask) | (unsigned)(lane << 14) | (unsigned)(s << 9) | (unsigned)((r4 >= 0) ? r4 : N));
             asm volatile("" : "+r"(kx[s]));          // keep it in a register (no re-derivation inside the scan loop)
         }
         unsigned live = exist;               // columns still in `remaining`
         double minVal = 0.0, rzmin = INFINITY;
-        int i = cur, lastk = N << 18;
+        int i = cur, lastk = N << kPosShift;
         unsigned mk;
-        int nsteps = 0;
         bool infeasible = false;
 
         // operands of the row about to be scanned: row dual, the row's deletion / insertion entry and (shared-memory store)
@@ -578,64 +629,32 @@ __device__ int lsape_warp(const Store &store, bool invalid, int n1, int n2, cons
         if (Store::kPrefetch && real) store.row_issue(i, cs);
 
         for (;;) {
-            ++nsteps;
-            int improved = 0;
-            unsigned lk = 0xffffffffu;
-            bool need_min = true;
-#if GED_LAP_SHORTCUT
+            unsigned keep = 0xffffffffu;     // 0 once this lane wrote a shortest-path cost below minVal (lap_relax_below)
+            unsigned lk;
             if (real) {                      // real row: n2 substitution entries + its own deletion entry
                 if (Store::kPrefetch) store.row_wait(i, cs);       // pairs with the row_issue of the previous step / prologue
                 else store.row(i, cs);
-                LapSlots<S>::relax_row_below(spc, pth, improved, v, cs, minVal, ui, i, live);
+                LapSlots<S>::relax_row_below(spc, pth, keep, v, cs, minVal, ui, i, live);
                 const double rd = __dsub_rn(__dadd_rn(minVal, (double)cx), ui);
-                LapSlots<S>::template relax_one_below<S, 2 * S>(spc, pth, improved, v, rd, i, (lane == (i & 31)) ? live : 0u, i >> 5, minVal);
+                LapSlots<S>::template relax_own_below<S, 2 * S>(spc, pth, keep, v, rd, i, live, i, lane, minVal);
             } else {                         // insertion row of column a0: its own entry + the zero block
                 const int a0 = i - n1;
                 const double ra = __dsub_rn(__dadd_rn(minVal, (double)cx), ui);
-                LapSlots<S>::template relax_one_below<0, S>(spc, pth, improved, v, ra, i, (lane == (a0 & 31)) ? live : 0u, a0 >> 5, minVal);
+                LapSlots<S>::template relax_own_below<0, S>(spc, pth, keep, v, ra, i, live, a0, lane, minVal);
                 // zero block: r = rz - v[j].  Rounding is monotone in rz, and after a scan with value rz0 every remaining
                 // deletion column has spc <= fl(rz0 - v[j]); a later insertion row with rz >= rz0 cannot lower any of them.
                 const double rz = __dsub_rn(__dadd_rn(minVal, 0.0), ui);
                 if (rz < rzmin) {
                     rzmin = rz;
-                    LapSlots<S>::template relax_base_below<S, 2 * S>(spc, pth, improved, v, rz, i, live, minVal);
+                    LapSlots<S>::template relax_base_below<S, 2 * S>(spc, pth, keep, v, rz, i, live, minVal);
                 }
             }
-            // Tie-break among the columns that attain the OLD minVal (see GED_LAP_SHORTCUT above): `improved` here means
-            // "this lane wrote a value below minVal" and bids key 0, below every real key.
+            // Tie-break among the columns that attain the OLD minVal (scan-step shortcut, see lap_relax_below): the bid starts
+            // from `keep`, so a lane that wrote a value below minVal bids key 0, below every real key.
+            lk = keep;
             LapSlots<S>::min_key(lk, spc, minVal, live, posk, kx);
-            lk = improved ? 0u : lk;
             mk = __reduce_min_sync(kFull, lk);
-            need_min = (mk - 1u >= 0xfffffffeu);
-#else
-            if (real) {                      // real row: n2 substitution entries + its own deletion entry
-                if (Store::kPrefetch) store.row_wait(i, cs);       // pairs with the row_issue of the previous step / prologue
-                else store.row(i, cs);
-                LapSlots<S>::relax_row(spc, pth, improved, v, cs, minVal, ui, i, live);
-                const double rd = __dsub_rn(__dadd_rn(minVal, (double)cx), ui);
-                LapSlots<S>::template relax_one<S, 2 * S, false>(spc, pth, improved, v, rd, i, (lane == (i & 31)) ? live : 0u, i >> 5);
-                // a real row almost always lowers something: recompute the minimum right away
-            } else {                         // insertion row of column a0: its own entry + the zero block
-                const int a0 = i - n1;
-                const double ra = __dsub_rn(__dadd_rn(minVal, (double)cx), ui);
-                LapSlots<S>::template relax_one<0, S>(spc, pth, improved, v, ra, i, (lane == (a0 & 31)) ? live : 0u, a0 >> 5);
-                // zero block: r = rz - v[j].  Rounding is monotone in rz, and after a scan with value rz0 every remaining
-                // deletion column has spc <= fl(rz0 - v[j]); a later insertion row with rz >= rz0 cannot lower any of them.
-                const double rz = __dsub_rn(__dadd_rn(minVal, 0.0), ui);
-                if (rz < rzmin) {
-                    rzmin = rz;
-                    LapSlots<S>::template relax_base<S, 2 * S>(spc, pth, improved, v, rz, i, live);
-                }
-                // Tie-break among the columns that still attain minVal.  If some shortest-path cost was lowered (that lane
-                // bids key 0, below every real key) or no remaining column attains minVal (all bids are ~0u), the minimum
-                // has to be recomputed first.
-                LapSlots<S>::min_key(lk, spc, minVal, live, posk, kx);
-                lk = improved ? 0u : lk;
-                mk = __reduce_min_sync(kFull, lk);
-                need_min = (mk - 1u >= 0xfffffffeu);
-            }
-#endif
-            if (need_min) {
+            if (mk - 1u >= 0xfffffffeu) {    // 0: some lane went below minVal; ~0: no remaining column attains minVal any more
                 double lmA = INFINITY, lmB = INFINITY;          // two independent chains
                 LapSlots<S>::min_value2(lmA, lmB, spc, live);
                 const double lm = (lmB < lmA) ? lmB : lmA;
@@ -649,30 +668,34 @@ __device__ int lsape_warp(const Store &store, bool invalid, int n1, int n2, cons
                 mk = __reduce_min_sync(kFull, lk);
                 const bool inf = (minVal == INFINITY);          // nothing reachable: leave the loop, report after it
                 infeasible |= inf;
-                mk = inf ? 0u : mk;
+                mk = inf ? (unsigned)N : mk;                    // row field N = "the search ends here"
             }
 
-            const int r4star = (int)(mk & 511u) - 1;
-            const unsigned lk_slot_bit = 1u << ((lk >> 14) & 15u);     // from the lane's own bid: ready before the reduction returns
-            {   // operands of the next row
-                const int in = max(r4star, 0);
+            int in = (int)(mk & 511u);                          // row matched with the winning column; N: it is unassigned
+            asm volatile("" : "+r"(in));                        // (addresses from `in`: one IMAD each instead of a second decode)
+            {   // operands of the next row (u[N], cdel[N] are padding)
                 real = in < n1;
                 ui = u[in];
                 cx = sm.cdel[in];
-                if (Store::kPrefetch && real && r4star >= 0) store.row_issue(in, cs);   // never leave a fetch in flight past the search
+                if (Store::kPrefetch && real) store.row_issue(in, cs);   // never leaves a fetch in flight past the search: N >= n1
             }
             // the winning column leaves `remaining`; the column at its end takes the freed position
-            lastk -= 1 << 18;
-            const int posstark = (int)((mk & 0xfffc0000u) ^ ((mk & (512u << 18)) ? (512u << 18) : (511u << 18)));
-            live &= ~((lk == mk) ? lk_slot_bit : 0u);
+            lastk -= 1 << kPosShift;
+            const int posstark = lap_winner_pos(mk, kPosMask);
+            // 1 << slot of the lane's own bid (ready before the reduction returns) leaves `live` in the lane that won
+            asm("{\n\t.reg .pred p;\n\t.reg .b32 g;\n\t"
+                "shf.l.wrap.b32 g, 0, %3, %4;\n\t"
+                "setp.eq.u32 p, %1, %2;\n\t"
+                "@p lop3.b32 %0, %0, g, 0, 0x30;\n\t}"
+                : "+r"(live) : "r"(lk), "r"(mk), "r"(one), "r"(lk >> 9));
 #pragma unroll
             for (int s = 0; s < 2 * S; ++s) posk[s] = (posk[s] == lastk) ? posstark : posk[s];
-            if (r4star < 0) break;
-            i = r4star;
+            if (in == N) break;
+            i = in;
         }
         if (infeasible) return GED_ST_INFEASIBLE;
-        steps += nsteps;
-        const int wl = (int)((mk >> 9) & 31u), ws = (int)((mk >> 14) & 15u);
+        steps += __reduce_add_sync(kFull, (unsigned)__popc(exist & ~live));   // every scan step removes exactly one column
+        const int wl = (int)((mk >> 14) & 31u), ws = (int)((mk >> 9) & 15u);
         const int sink = (ws < S) ? (wl + 32 * ws) : (n2 + wl + 32 * (ws - S));
 
         // dual update (scipy solve(): u[cur] += minVal; u[i] += minVal - spc[col4row[i]]; v[j] -= minVal - spc[j]);
@@ -684,7 +707,7 @@ __device__ int lsape_warp(const Store &store, bool invalid, int n1, int n2, cons
                 const int j = (s < S) ? (lane + 32 * s) : (n2 + lane + 32 * (s - S));
                 const double delta = __dsub_rn(minVal, spc[s]);
                 v[s] = __dsub_rn(v[s], delta);
-                const int r4 = (kx[s] & 511) - 1;
+                const int r4 = kx[s] & 511;
                 if (j != sink) u[r4] = __dadd_rn(u[r4], delta);
                 sm.path[j] = (int16_t)pth[s];
             }
@@ -1433,6 +1456,9 @@ __device__ int lsape_team(const float *cost, bool invalid, int n1, int n2, const
     __syncthreads();
     const float *ccol = cost + aR;                            // element (i, aR) at ccol[i * n2]
 
+    // tie-break keys as in lsape_warp (assigned << 31 | kk << 19 | lane << 14 | slot << 9 | row), slot = s << 4 | the column
+    // group's index among the 2 W groups of the team (s = 0: real columns of warp w, 1: its deletion columns)
+    constexpr unsigned kPosShift = 19, kPosMask = 511u << kPosShift;
     unsigned long long steps = 0;
     for (int cur = 0; cur < N; ++cur) {
         double spc[2];
@@ -1442,15 +1468,16 @@ __device__ int lsape_team(const float *cost, bool invalid, int n1, int n2, const
             const int j = s ? n2 + aR : aR;
             spc[s] = INFINITY;
             pth[s] = -1;
-            posk[s] = (N - 1 - j) << 18;
+            posk[s] = (N - 1 - j) << kPosShift;
             int r4 = -1;
             if ((exist >> s) & 1u) r4 = sm.row4col[j];
-            kx[s] = (((r4 >= 0) ? 512 : 511) << 18) | ((s ? W + w : w) << 14) | (lane << 9) | (r4 + 1);
+            kx[s] = (int)(((r4 >= 0) ? 0x80000000u : kPosMask) | (unsigned)(lane << 14) | (unsigned)((s ? 16 + W + w : w) << 9) |
+                          (unsigned)((r4 >= 0) ? r4 : N));
             asm volatile("" : "+r"(kx[s]));
         }
         unsigned live = exist;
         double minVal = 0.0, rzmin = INFINITY;
-        int i = cur, lastk = N << 18;
+        int i = cur, lastk = N << kPosShift;
         unsigned mk;
         int nsteps = 0;
         bool infeasible = false;
@@ -1462,24 +1489,24 @@ __device__ int lsape_team(const float *cost, bool invalid, int n1, int n2, const
 
         for (;;) {
             ++nsteps;
-            int improved = 0;
-            unsigned lk = 0xffffffffu;
+            unsigned keep = 0xffffffffu;     // 0 once this lane wrote a shortest-path cost below minVal (lap_relax_below)
+            unsigned lk;
             if (real) {                      // real row: this warp's 32 substitution entries; the deletion entry at its owner
-                LapSlots<1>::relax_row_below(spc, pth, improved, v, cs, minVal, ui, i, live);
+                LapSlots<1>::relax_row_below(spc, pth, keep, v, cs, minVal, ui, i, live);
                 const double rd = __dsub_rn(__dadd_rn(minVal, (double)cx), ui);
-                LapSlots<1>::template relax_base_below<1, 2>(spc, pth, improved, v, rd, i, (aR == i) ? live : 0u, minVal);
+                lap_relax_own_below<2u>(spc[1], pth[1], keep, __dsub_rn(rd, v[1]), i, live, minVal, i, aR);
             } else {                         // insertion row of column a0: its own entry at its owner + the zero block
                 const int a0 = i - n1;
                 const double ra = __dsub_rn(__dadd_rn(minVal, (double)cx), ui);
-                LapSlots<1>::template relax_base_below<0, 1>(spc, pth, improved, v, ra, i, (aR == a0) ? live : 0u, minVal);
+                lap_relax_own_below<1u>(spc[0], pth[0], keep, __dsub_rn(ra, v[0]), i, live, minVal, a0, aR);
                 const double rz = __dsub_rn(__dadd_rn(minVal, 0.0), ui);
                 if (rz < rzmin) {
                     rzmin = rz;
-                    LapSlots<1>::template relax_base_below<1, 2>(spc, pth, improved, v, rz, i, live, minVal);
+                    LapSlots<1>::template relax_base_below<1, 2>(spc, pth, keep, v, rz, i, live, minVal);
                 }
             }
+            lk = keep;                       // a lane that went below minVal bids key 0
             LapSlots<1>::min_key(lk, spc, minVal, live, posk, kx);
-            lk = improved ? 0u : lk;
             mk = team_min_key<W>(__reduce_min_sync(kFull, lk), xch, xp);
             if (mk - 1u >= 0xfffffffeu) {    // some value fell below minVal (bid 0) or no column attains it (all bids ~0)
                 double lmA = INFINITY, lmB = INFINITY;
@@ -1496,29 +1523,28 @@ __device__ int lsape_team(const float *cost, bool invalid, int n1, int n2, const
                 mk = team_min_key<W>(__reduce_min_sync(kFull, lk), xch, xp);
                 const bool inf = (minVal == INFINITY);
                 infeasible |= inf;
-                mk = inf ? 0u : mk;
+                mk = inf ? (unsigned)N : mk;                    // row field N = "the search ends here"
             }
 
-            const int r4star = (int)(mk & 511u) - 1;
-            const unsigned lk_slot_bit = (((lk >> 14) & 15u) >= (unsigned)W) ? 2u : 1u;
-            {   // operands of the next row
-                const int in = max(r4star, 0);
+            int in = (int)(mk & 511u);                          // row matched with the winning column; N: it is unassigned
+            asm volatile("" : "+r"(in));                        // (addresses from `in`: one IMAD each instead of a second decode)
+            {   // operands of the next row (u[N], cdel[N] are padding)
                 real = in < n1;
                 ui = u[in];
                 cx = sm.cdel[in];
-                if (real && r4star >= 0) cs[0] = ccol[in * n2];
+                if (real) cs[0] = ccol[in * n2];
             }
-            lastk -= 1 << 18;
-            const int posstark = (int)((mk & 0xfffc0000u) ^ ((mk & (512u << 18)) ? (512u << 18) : (511u << 18)));
-            live &= ~((lk == mk) ? lk_slot_bit : 0u);
+            lastk -= 1 << kPosShift;
+            const int posstark = lap_winner_pos(mk, kPosMask);
+            live &= ~((lk == mk) ? ((lk & (16u << 9)) ? 2u : 1u) : 0u);
 #pragma unroll
             for (int s = 0; s < 2; ++s) posk[s] = (posk[s] == lastk) ? posstark : posk[s];
-            if (r4star < 0) break;
-            i = r4star;
+            if (in == N) break;
+            i = in;
         }
         if (infeasible) return GED_ST_INFEASIBLE;
         steps += nsteps;
-        const int wl = (int)((mk >> 9) & 31u), ws = (int)((mk >> 14) & 15u);
+        const int wl = (int)((mk >> 14) & 31u), ws = (int)((mk >> 9) & 15u);
         const int sink = (ws < W) ? (wl + 32 * ws) : (n2 + wl + 32 * (ws - W));
 
 #pragma unroll
@@ -1528,7 +1554,7 @@ __device__ int lsape_team(const float *cost, bool invalid, int n1, int n2, const
                 const int j = s ? n2 + aR : aR;
                 const double delta = __dsub_rn(minVal, spc[s]);
                 v[s] = __dsub_rn(v[s], delta);
-                const int r4 = (kx[s] & 511) - 1;
+                const int r4 = kx[s] & 511;
                 if (j != sink) u[r4] = __dadd_rn(u[r4], delta);          // distinct rows: every column has its own row4col
                 sm.path[j] = (int16_t)pth[s];
             }
