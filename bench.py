@@ -258,6 +258,11 @@ def issue_peaks():
         return None, "unavailable"
 
 
+def library_version():
+    from ppo_bihyb_b200 import _lib
+    return _lib.load().ged_version().decode()
+
+
 def issue_roofline(args, world, kernel_ms, lap_steps_per_step):
     """The binding roof of ged_solve_kernel is instruction issue (its busiest unit: the ALU pipe), not HBM or tensor cores
     (DESIGN.md section 5).  achieved = warp instructions the step's solve launches EXECUTE (ncu smsp__inst_executed.sum of
@@ -283,6 +288,7 @@ def issue_roofline(args, world, kernel_ms, lap_steps_per_step):
         roof.update({"achieved": inst / (kernel_ms * 1e-3), "frac": inst / (kernel_ms * 1e-3) / peaks["fma_winst_per_s"],
                      "traffic": w.get("dram_bytes_per_step"), "warp_instructions_per_step": inst,
                      "instructions_source": f"ncu smsp__inst_executed.sum over the step's launches, {w.get('source')}",
+                     "instructions_counted_on": w.get("library"), "library": library_version(),
                      "alu_pipe": {"achieved": w["alu_warp_instructions_per_step"] / (kernel_ms * 1e-3),
                                   "peak": peaks["alu_winst_per_s"], "unit": "warp-instructions/s",
                                   "frac": w["alu_warp_instructions_per_step"] / (kernel_ms * 1e-3) / peaks["alu_winst_per_s"]},

@@ -351,16 +351,13 @@ __device__ __forceinline__ double double_from_ord(unsigned ohi, unsigned olo)
 // ---- per-slot building blocks of the LAP scan step, written as PTX so that each is exactly the intended handful of
 // SASS instructions (LOP3 -> predicate, DSETP with the predicate folded in, selects) without moves or branches -----------
 
-// Scan-step shortcut (GED_LAP_SHORTCUT, default on).  Every shortest-path cost of a column still in `remaining` is >= minVal
-// (minVal was their minimum when it was set, and only a relaxation changes one afterwards), so after a row's relaxations the
-// new minimum is minVal itself unless (a) a value written by this row is BELOW minVal (possible through rounding only, and at
-// the first row of a search, where minVal = 0) or (b) no remaining column attains minVal any more.  minVal stays the same in
-// 89 % of the scan steps of an AIDS-50+ solve, so a step first bids for the tie-break key at the OLD minVal -- a lane that saw
-// (a) bids key 0 -- and only recomputes the 64-bit minimum (two more warp reductions, the order-preserving split, the
-// per-slot minimum chain) when the winning bid is 0 (a) or ~0 (b).
-#ifndef GED_LAP_SHORTCUT
-#define GED_LAP_SHORTCUT 1
-#endif
+// Scan-step shortcut.  Every shortest-path cost of a column still in `remaining` is >= minVal (minVal was their minimum when
+// it was set, and only a relaxation changes one afterwards), so after a row's relaxations the new minimum is minVal itself
+// unless (a) a value written by this row is BELOW minVal (possible through rounding only, and at the first row of a search,
+// where minVal = 0) or (b) no remaining column attains minVal any more.  minVal stays the same in 89 % of the scan steps of an
+// AIDS-50+ solve, so a step first bids for the tie-break key at the OLD minVal -- a lane that saw (a) bids key 0 -- and only
+// recomputes the 64-bit minimum (two more warp reductions, the order-preserving split, the per-slot minimum chain) when the
+// winning bid is 0 (a) or ~0 (b).  (A/B against the plain form: profiles/r02a_ab_lap_shortcut.md.)
 
 // if (live & MASK) && r < spc:  spc = r, pth = i, and keep = 0 if also r < minVal.  `keep` starts a scan step as ~0 and is the
 // start value of the lane's tie-break bid (a minimum of keys), so a lane that wrote a value below minVal bids key 0 for free.
@@ -397,28 +394,6 @@ __device__ __forceinline__ void lap_relax_own_below(double &spc, int &pth, unsig
         : "+d"(spc), "+r"(pth), "+r"(keep) : "d"(r), "r"(i), "r"(live), "n"(MASK), "d"(minVal), "r"(k), "r"(id));
 }
 
-// if (live & MASK) && r < spc:  spc = r, pth = i (and, when TRACK, improved = 1)
-template <unsigned MASK, bool TRACK = true>
-__device__ __forceinline__ void lap_relax(double &spc, int &pth, int &improved, double r, int i, unsigned live)
-{
-    if constexpr (TRACK)
-        asm("{\n\t.reg .pred q, p;\n\t.reg .b32 t;\n\t"
-            "and.b32 t, %5, %6;\n\t"
-            "setp.ne.u32 q, t, 0;\n\t"
-            "setp.lt.and.f64 p, %3, %0, q;\n\t"
-            "selp.f64 %0, %3, %0, p;\n\t"
-            "selp.b32 %1, %4, %1, p;\n\t"
-            "@p mov.b32 %2, 1;\n\t}"
-            : "+d"(spc), "+r"(pth), "+r"(improved) : "d"(r), "r"(i), "r"(live), "n"(MASK));
-    else
-        asm("{\n\t.reg .pred q, p;\n\t.reg .b32 t;\n\t"
-            "and.b32 t, %4, %5;\n\t"
-            "setp.ne.u32 q, t, 0;\n\t"
-            "setp.lt.and.f64 p, %2, %0, q;\n\t"
-            "selp.f64 %0, %2, %0, p;\n\t"
-            "selp.b32 %1, %3, %1, p;\n\t}"
-            : "+d"(spc), "+r"(pth) : "d"(r), "r"(i), "r"(live), "n"(MASK));
-}
 // if (live & MASK) && spc < lm:  lm = spc
 template <unsigned MASK>
 __device__ __forceinline__ void lap_min_value(double &lm, double spc, unsigned live)
@@ -458,39 +433,7 @@ __device__ __forceinline__ int lap_winner_pos(unsigned mk, unsigned mask)
 
 template <int S, int I = 0>
 struct LapSlots {
-    // slots [LO, HI): relax with r = base - v[slot]
-    template <int LO, int HI, bool TRACK = true>
-    static __device__ __forceinline__ void relax_base(double (&spc)[2 * S], int (&pth)[2 * S], int &improved,
-                                                      const double (&v)[2 * S], double base, int i, unsigned live)
-    {
-        if constexpr (I < 2 * S) {
-            if constexpr (I >= LO && I < HI)
-                lap_relax<(1u << I), TRACK>(spc[I], pth[I], improved, __dsub_rn(base, v[I]), i, live);
-            LapSlots<S, I + 1>::template relax_base<LO, HI, TRACK>(spc, pth, improved, v, base, i, live);
-        }
-    }
-    // exactly one slot of [LO, HI) -- slot LO + sel, sel warp-uniform -- is relaxed (the row's own deletion / insertion
-    // entry): all slots of the group run under a lane mask, or (GED_RELAX_BRANCH_MIN_S) a warp-uniform branch picks the slot.
-    template <int LO, int HI, bool TRACK = true>
-    static __device__ __forceinline__ void relax_one(double (&spc)[2 * S], int (&pth)[2 * S], int &improved,
-                                                     const double (&v)[2 * S], double base, int i, unsigned live_lane, int sel)
-    {
-#ifndef GED_RELAX_BRANCH_MIN_S
-#define GED_RELAX_BRANCH_MIN_S 9          // measured (n=80, n=100): the masked all-slots form is faster than the branch at every S
-#endif
-        if constexpr (S < GED_RELAX_BRANCH_MIN_S) {
-            relax_base<LO, HI, TRACK>(spc, pth, improved, v, base, i, live_lane & ((1u << LO) << sel));
-        } else if constexpr (I < 2 * S) {
-            if constexpr (I >= LO && I < HI) {
-                if (sel == I - LO) {
-                    lap_relax<(1u << I), TRACK>(spc[I], pth[I], improved, __dsub_rn(base, v[I]), i, live_lane);
-                    return;
-                }
-            }
-            LapSlots<S, I + 1>::template relax_one<LO, HI, TRACK>(spc, pth, improved, v, base, i, live_lane, sel);
-        }
-    }
-    // the same three with the `below` flag of the scan-step shortcut (see lap_relax_below)
+    // slots [LO, HI): relax with r = base - v[slot] (see lap_relax_below)
     template <int LO, int HI>
     static __device__ __forceinline__ void relax_base_below(double (&spc)[2 * S], int (&pth)[2 * S], unsigned &below,
                                                             const double (&v)[2 * S], double base, int i, unsigned live, double minVal)
@@ -500,13 +443,6 @@ struct LapSlots {
                 lap_relax_below<(1u << I)>(spc[I], pth[I], below, __dsub_rn(base, v[I]), i, live, minVal);
             LapSlots<S, I + 1>::template relax_base_below<LO, HI>(spc, pth, below, v, base, i, live, minVal);
         }
-    }
-    template <int LO, int HI>
-    static __device__ __forceinline__ void relax_one_below(double (&spc)[2 * S], int (&pth)[2 * S], unsigned &below,
-                                                           const double (&v)[2 * S], double base, int i, unsigned live_lane, int sel,
-                                                           double minVal)
-    {
-        relax_base_below<LO, HI>(spc, pth, below, v, base, i, live_lane & ((1u << LO) << sel), minVal);
     }
     // slots [LO, HI) hold columns lane, lane + 32, ... of one group: relax the one that is column k of the group
     template <int LO, int HI>
@@ -528,17 +464,6 @@ struct LapSlots {
             const double r = __dsub_rn(__dsub_rn(__dadd_rn(minVal, (double)cs[I]), ui), v[I]);
             lap_relax_below<(1u << I)>(spc[I], pth[I], below, r, i, live, minVal);
             LapSlots<S, I + 1>::relax_row_below(spc, pth, below, v, cs, minVal, ui, i, live);
-        }
-    }
-    // real slots [0, S): relax with SciPy's r = ((minVal + c) - u[i]) - v[j]
-    static __device__ __forceinline__ void relax_row(double (&spc)[2 * S], int (&pth)[2 * S], int &improved,
-                                                     const double (&v)[2 * S], const float (&cs)[S], double minVal, double ui,
-                                                     int i, unsigned live)
-    {
-        if constexpr (I < S) {
-            const double r = __dsub_rn(__dsub_rn(__dadd_rn(minVal, (double)cs[I]), ui), v[I]);
-            lap_relax<(1u << I), false>(spc[I], pth[I], improved, r, i, live);
-            LapSlots<S, I + 1>::relax_row(spc, pth, improved, v, cs, minVal, ui, i, live);
         }
     }
     static __device__ __forceinline__ void min_value2(double &lmA, double &lmB, const double (&spc)[2 * S], unsigned live)
@@ -2715,7 +2640,7 @@ int64_t ged_solve_smem_bytes(int32_t max_n1, int32_t max_n2)
 }
 
 int ged_abi_version(void) { return GED_ABI_VERSION; }
-const char *ged_version(void) { return "ged_b200 0.5.0 (sm_100a; ABI 8; canonical order v2; tensor-memory cost store; persistent work-queue launches; CTA-per-candidate team launches)"; }
+const char *ged_version(void) { return "ged_b200 0.6.0 (sm_100a; ABI 8; canonical order v2; tensor-memory cost store; persistent work-queue launches; CTA-per-candidate team launches)"; }
 const char *ged_last_error(void) { return g_err; }
 
 }  // extern "C"
