@@ -184,3 +184,16 @@ def test_dense_k_factor_cache_does_not_alias_freed_tensors():
     was = float(k4[0, n2, 1, n2])
     k4[0, n2, 1, n2] = 1.0 - was            # breaks the symmetry of A1 -> not a construct_k matrix any more
     assert _DenseKFactors.get(k, n1, n2) is None and f0 is not None
+
+
+def test_stored_instruction_counts_belong_to_the_built_library():
+    """bench.py's roofline divides instruction counts stored in profiles/roofline_r02.json (ncu of the bench mix) by the step
+    time it measures: the counts must have been taken on the library that is built from this tree."""
+    import json
+    from ppo_bihyb_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    prof = json.load(open(os.path.join(root, "profiles", "roofline_r02.json")))
+    version = _lib.load().ged_version().decode()
+    for sig, w in prof["workloads"].items():
+        assert w.get("library") == version, (sig, w.get("library"), version)
+        assert w["warp_instructions_per_step"] == sum(c["warp_instructions"] for c in w["per_class"])
