@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GED_ABI_VERSION 8
+#define GED_ABI_VERSION 9
 
 /* call-level errors */
 #define GED_OK 0
@@ -83,7 +83,7 @@ typedef struct ged_solve_desc {
     int64_t mat_stride;      /* elements between consecutive candidates in x_init / x_out / workspace / trace;
                                 must be >= (max_n1+1)*(max_n2+1) */
     /* Scratch for the fractional iterate X and X*A2^T of the solves in flight (touched only between LAPs, L2 resident):
-     * `workspace_slots` rows of 2 * workspace_stride floats.  A solve claims a free row for its lifetime with an atomic
+     * `workspace_slots` rows of 2 (or workspace_mats) * workspace_stride floats.  A solve claims a free row for its lifetime with an atomic
      * compare-and-swap on workspace_locks[row] (int32, zero-initialised by the caller, zero again when the launch ends),
      * so the footprint follows the solves RESIDENT on the device (ged_solve_max_resident), not the batch size.
      * workspace_slots == 0: legacy layout, row b belongs to candidate b (B rows, no locks).
@@ -112,6 +112,11 @@ typedef struct ged_solve_desc {
      * to 32 nodes keep a one-warp LAP with three helper warps for K.X and the update (1.15x; calls of <= 512 candidates).
      * Results are bit-identical under every hint. */
     int32_t launch_hint;
+    /* Matrices per workspace row: 0 / 2 = the row holds X and X*A2^T (2 * workspace_stride floats), 3 = it holds a third
+     * matrix of workspace_stride floats (ABI 9).  With the third matrix a throughput launch of pairs above 64 nodes -- where
+     * tensor memory and shared memory together hold the LAP cost matrices of only 12 solves per SM -- runs additional warps
+     * whose cost matrix lives there (L2 resident): 16 solves per SM, +12 % at 80 nodes.  Results are bit-identical. */
+    int32_t workspace_mats;
 } ged_solve_desc;
 
 typedef struct ged_solve_out {

@@ -19,7 +19,7 @@ c_u64p = ctypes.POINTER(ctypes.c_ulonglong)
 GED_OK, GED_E_BADARG, GED_E_TOO_LARGE, GED_E_CUDA = 0, 1, 2, 3
 GED_ST_INVALID_COST, GED_ST_INFEASIBLE, GED_ST_BAD_GRAPH = 1, 2, 4
 GED_SOLVER_IPFP, GED_SOLVER_HUNGARIAN = 0, 1
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 # every symbol include/ged_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED_SYMBOLS = (
@@ -63,6 +63,7 @@ class GedSolveDesc(ctypes.Structure):
         ("order_count", ctypes.c_int32),
         ("work_counter", c_i32p),
         ("launch_hint", ctypes.c_int32),
+        ("workspace_mats", ctypes.c_int32),
     ]
 
 

@@ -168,6 +168,33 @@ struct SmemCost {
     __device__ __forceinline__ void row_issue(int i, float (&cs)[S]) const { row(i, cs); }
     __device__ __forceinline__ void row_wait(int, float (&)[S]) const {}
     __device__ __forceinline__ void flush() const { __syncwarp(); }
+    __device__ __forceinline__ void bind_global(float *) {}
+};
+
+// The same layout in GLOBAL memory (the third matrix of the solve's scratch row, L2 / L1 resident): the store of the extra
+// warps of a hybrid CTA that neither tensor memory nor shared memory has room for.  A row costs an L2 round trip (issued a
+// step ahead, like the shared-memory row), so such a warp runs at roughly 0.6 of a shared-memory warp's speed -- it pays as
+// an ADDITIONAL warp on an SM whose issue slots are half idle (profiles/r02o_ab_gmem_experiment.md), never as a replacement.
+template <int S>
+struct GmemCost {
+    static constexpr bool kPrefetch = true;
+    float *base;
+    int stride;                              // = n2
+    __device__ __forceinline__ void put(int i, int s, float v) const
+    {
+        const int a = (threadIdx.x & 31) + 32 * s;
+        if (a < stride) base[i * stride + a] = v;
+    }
+    __device__ __forceinline__ void row(int i, float (&cs)[S]) const
+    {
+        const float *p = base + i * stride + (threadIdx.x & 31);
+#pragma unroll
+        for (int s = 0; s < S; ++s) cs[s] = p[32 * s];       // lanes past n2 read don't-care values inside the scratch row
+    }
+    __device__ __forceinline__ void row_issue(int i, float (&cs)[S]) const { row(i, cs); }
+    __device__ __forceinline__ void row_wait(int, float (&)[S]) const {}
+    __device__ __forceinline__ void flush() const { __syncwarp(); }
+    __device__ __forceinline__ void bind_global(float *p) { base = p; }
 };
 
 template <int S>
@@ -245,19 +272,21 @@ struct TmemCost {
                          : "+f"(cs[0]), "+f"(cs[1]), "+f"(cs[2]), "+f"(cs[3]), "+f"(cs[4]), "+f"(cs[5]), "+f"(cs[6])::"memory");
     }
     __device__ __forceinline__ void flush() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+    __device__ __forceinline__ void bind_global(float *) {}
 };
 
-// Hybrid CTAs (tensor-memory warps + shared-memory warps side by side) run ONE instantiation of the solve for both kinds
-// of warp: the store is chosen by a warp-uniform flag at each access.  Two instantiations would double the hot code
-// (IPFP iteration body ~59 KB each) and the two kinds of warp then evict each other's loops from the 32 KB instruction
-// cache (ncu: stall_no_instruction 0.12 -> 1.04 per issue, no gain from the extra warps).  Prefetch policy per kind is
-// kept: the shared-memory row is issued a step ahead (row_issue), the tensor-memory row is fetched where it is
-// consumed (row_wait carries the row index for that).
-template <int S>
+// Hybrid CTAs (tensor-memory warps next to warps of a second store M: shared memory, or global memory) run ONE instantiation
+// of the solve for both kinds of warp: the store is chosen by a warp-uniform flag at each access.  Two instantiations would
+// double the hot code (IPFP iteration body ~59 KB each) and the two kinds of warp then evict each other's loops from the 32 KB
+// instruction cache (ncu: stall_no_instruction 0.12 -> 1.04 per issue, no gain from the extra warps); for the same reason a
+// CTA mixes tensor memory with ONE other store, not both (a three-way store made every hybrid launch 5-11 % slower,
+// profiles/r02p_ab_gmem_threeway.md).  Prefetch policy per kind is kept: the shared- / global-memory row is issued a step
+// ahead (row_issue), the tensor-memory row is fetched where it is consumed (row_wait carries the row index for that).
+template <int S, class M>
 struct AnyCost {
     static constexpr bool kPrefetch = true;
     TmemCost<S> t;
-    SmemCost<S> m;
+    M m;
     bool tm;                                 // warp-uniform
     __device__ __forceinline__ void put(int i, int s, float v) const
     {
@@ -282,6 +311,7 @@ struct AnyCost {
         if (tm) t.flush();
         else m.flush();
     }
+    __device__ __forceinline__ void bind_global(float *p) { m.bind_global(p); }
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -991,6 +1021,7 @@ struct SolveParams {
     int spread;              // static assignment: 1 = candidate blockIdx + warp * gridDim (spread over CTAs), 0 = CTA-major
     int tmem_warps;          // 0 or 4: warps 0..3 of every CTA keep their cost matrix in tensor memory
     int tmem_cols;           // columns allocated per CTA (power of two >= 32)
+    int ws_mats;             // matrices per scratch row: 2 (X, X A2^T) or 3 (+ a cost matrix for a global-memory warp)
     ged_solve_out out;
     SliceLayout layout;
 };
@@ -1020,7 +1051,7 @@ __device__ inline void load_pair(const ged_pairs &pp, int p, const Slice &sm, Pa
 
 // One candidate solve by one warp: GEDenv.step :110-124 -> solve_feasible_ged :140-158 -> ipfp_ged :256-289.
 template <int S, class Store>
-__device__ void solve_one(const SolveParams &prm, int b, int slot, const Slice &sm, const Store &store)
+__device__ void solve_one(const SolveParams &prm, int b, int slot, const Slice &sm, const Store &store_in)
 {
     const int lane = threadIdx.x & 31;
     const ged_solve_out &out = prm.out;
@@ -1059,8 +1090,10 @@ __device__ void solve_one(const SolveParams &prm, int b, int slot, const Slice &
         }
         ws_row = __shfl_sync(kFull, ws_row, 0);
     }
-    float *X = prm.workspace ? prm.workspace + (long long)ws_row * 2 * prm.ws_stride : nullptr;
+    float *X = prm.workspace ? prm.workspace + (long long)ws_row * prm.ws_mats * prm.ws_stride : nullptr;
     float *Y = X ? X + prm.ws_stride : nullptr;
+    Store store = store_in;                  // a global-memory warp's cost matrix is the third matrix of its scratch row
+    store.bind_global(X && prm.ws_mats >= 3 ? X + 2 * prm.ws_stride : nullptr);
     unsigned long long lap_steps = 0;
     int iters = 0;
     double best_ub = INFINITY;
@@ -1221,15 +1254,16 @@ constexpr int kMaxCtaWarps = 8;          // 4 tensor-memory warps + at most 4 sh
 #define GED_SPREAD_ROTATE 1
 #endif
 static __device__ int g_sm_tickets[256];
-constexpr int kModeSmem = 0, kModeTmem = 1, kModeHybrid = 2;   // cost store of the CTA's warps: all shared / all tensor memory / both
+// cost store of the CTA's warps: all shared memory / all tensor memory / tensor + shared memory / tensor + global memory
+constexpr int kModeSmem = 0, kModeTmem = 1, kModeHybrid = 2, kModeHybridG = 3;
 
 // S <= 3 (pairs up to 96 nodes): two 8-warp CTAs, or four 4-warp CTAs, must fit the register file -> at most 128 registers
 // per thread (registers are allocated per CTA in units of 4 warps: a 7-warp CTA at 136 registers is alone on its SM).
 #ifndef GED_TMEM_CTAS_S2
 #define GED_TMEM_CTAS_S2 0               // experiment: > 0 = launch bounds (128 threads, that many CTAs per SM) for the S <= 2 tensor-memory kernel
 #endif
-#define GED_LB_THREADS(S_, MODE_) ((GED_TMEM_CTAS_S2 > 0 && (S_) <= 2 && (MODE_) != kModeHybrid) ? 32 * kTmemWarps : 32 * kMaxCtaWarps)
-#define GED_LB_CTAS(S_, MODE_) ((GED_TMEM_CTAS_S2 > 0 && (S_) <= 2 && (MODE_) != kModeHybrid) ? GED_TMEM_CTAS_S2 : ((S_) <= 3 ? 2 : 1))
+#define GED_LB_THREADS(S_, MODE_) ((GED_TMEM_CTAS_S2 > 0 && (S_) <= 2 && (MODE_) < kModeHybrid) ? 32 * kTmemWarps : 32 * kMaxCtaWarps)
+#define GED_LB_CTAS(S_, MODE_) ((GED_TMEM_CTAS_S2 > 0 && (S_) <= 2 && (MODE_) < kModeHybrid) ? GED_TMEM_CTAS_S2 : ((S_) <= 3 ? 2 : 1))
 template <int S, int MODE>
 __global__ void __launch_bounds__(GED_LB_THREADS(S, MODE), GED_LB_CTAS(S, MODE)) ged_solve_kernel(SolveParams prm)
 {
@@ -1255,9 +1289,11 @@ __global__ void __launch_bounds__(GED_LB_THREADS(S, MODE), GED_LB_CTAS(S, MODE))
     const int gwarp = blockIdx.x * nwarps + warp;
     const int m1 = prm.pairs.max_n1, m2 = prm.pairs.max_n2;
     const bool tm = TM && warp < nt;         // this warp keeps its cost matrix in tensor memory (lane quarter = warp id)
-    const Slice sm = tm ? carve(smem_raw + (size_t)warp * prm.layout.bytes, prm.layout, m1, m2, false)
-                        : carve(smem_raw + (size_t)nt * prm.layout.bytes + (size_t)(warp - nt) * (prm.layout.bytes + prm.layout.cost_bytes),
-                                prm.layout, m1, m2, true);
+    // the other warps: in shared memory behind their slice, or (kModeHybridG) in global memory -- slice only
+    const Slice sm = (tm || MODE == kModeHybridG)
+                         ? carve(smem_raw + (size_t)warp * prm.layout.bytes, prm.layout, m1, m2, false)
+                         : carve(smem_raw + (size_t)nt * prm.layout.bytes + (size_t)(warp - nt) * (prm.layout.bytes + prm.layout.cost_bytes),
+                                 prm.layout, m1, m2, true);
     uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16);
     asm volatile("" : "+r"(taddr));          // opaque: kept in a register instead of being re-derived from %tid per row fetch
     int vwarp = warp;                        // position of this warp in the static assignment
@@ -1285,7 +1321,10 @@ __global__ void __launch_bounds__(GED_LB_THREADS(S, MODE), GED_LB_CTAS(S, MODE))
             TmemCost<S> store{taddr};
             solve_one<S>(prm, b, gwarp, sm, store);
         } else if constexpr (MODE == kModeHybrid) {
-            AnyCost<S> store{TmemCost<S>{taddr}, SmemCost<S>{sm.cost, n2}, tm};
+            AnyCost<S, SmemCost<S>> store{TmemCost<S>{taddr}, SmemCost<S>{sm.cost, n2}, tm};
+            solve_one<S>(prm, b, gwarp, sm, store);
+        } else if constexpr (MODE == kModeHybridG) {
+            AnyCost<S, GmemCost<S>> store{TmemCost<S>{taddr}, GmemCost<S>{nullptr, n2}, tm};
             solve_one<S>(prm, b, gwarp, sm, store);
         } else {
             SmemCost<S> store{sm.cost, n2};
@@ -1762,7 +1801,7 @@ __device__ void solve_team(const SolveParams &prm, int b, const Slice &sm, float
     }
     __syncthreads();
     const int ws_row = xch->ws_row;
-    float *X = prm.workspace ? prm.workspace + (long long)ws_row * 2 * prm.ws_stride : nullptr;
+    float *X = prm.workspace ? prm.workspace + (long long)ws_row * prm.ws_mats * prm.ws_stride : nullptr;
     float *Y = X ? X + prm.ws_stride : nullptr;
     unsigned long long lap_steps = 0;
     int iters = 0;
@@ -2188,11 +2227,13 @@ int launch_uniform(KernelT kernel, const ParamsT &prm, int count, int slice_byte
 
 // Shape of the hybrid CTA of the solve kernel (see the file header): 4 tensor-memory-backed warps + k shared-memory-
 // backed warps, sized so that shared memory and tensor-memory columns run out together.
-struct CtaShape { int tmem_warps, tmem_cols, smem_warps, smem_bytes; };
+struct CtaShape { int tmem_warps, tmem_cols, smem_warps, smem_bytes, gmem_warps; };
 
-static CtaShape plan_cta(const SliceLayout &L, int max_n1, int S, int regs_per_thread, bool prefer_smem = false)
+// allow_gmem: the caller's scratch rows hold a third matrix (ged_solve_desc.workspace_mats >= 3), so the warp slots that
+// registers and the launch bounds leave after the shared-memory warps can be filled with global-memory warps.
+static CtaShape plan_cta(const SliceLayout &L, int max_n1, int S, int regs_per_thread, bool prefer_smem = false, bool allow_gmem = false)
 {
-    CtaShape c{0, 0, 1, 0};
+    CtaShape c{0, 0, 1, 0, 0};
     const int big = L.bytes + L.cost_bytes;
     const int mode = env_int("GED_B200_COST_STORE", prefer_smem ? 0 : 2);   // 0: shared memory only, 1: tensor memory only, 2: hybrid
     int cols = 32;
@@ -2212,10 +2253,21 @@ static CtaShape plan_cta(const SliceLayout &L, int max_n1, int S, int regs_per_t
         const int kforce = env_int("GED_B200_SMEM_WARPS", -1);
         if (kforce >= 0) { k = (budget - kTmemWarps * L.bytes) / big; if (k > kmax) k = kmax; if (kforce < k) k = kforce; }
         if (k >= 0) {
+            // Global-memory warps INSTEAD of the shared-memory ones where that puts at least a third more warps on the SM:
+            // measured (profiles/r02o_ab_gmem_experiment.md) 16 global-hybrid against 12 shared-hybrid warps per SM is +12 % at
+            // 80 nodes, 16 against 14 is -1 % (70 nodes), 8 against 7 is -9 % (100 nodes) -- a global-memory warp runs at
+            // roughly 0.6 of a shared-memory warp's speed, it pays as an additional warp only.
+            int g = 0;
+            if (allow_gmem && mode == 2 && q == 2 && kmax > 0 && env_int("GED_B200_GMEM_WARPS", 1)) {   // (q == 1: not measured)
+                int kg = (budget - kTmemWarps * L.bytes) / L.bytes;
+                if (kg > kmax) kg = kmax;
+                if (3 * (kTmemWarps + kg) >= 4 * (kTmemWarps + k)) { g = kg; k = 0; }
+            }
             c.tmem_warps = kTmemWarps;
             c.tmem_cols = cols;
             c.smem_warps = k;
-            c.smem_bytes = kTmemWarps * L.bytes + k * big;
+            c.gmem_warps = g;
+            c.smem_bytes = kTmemWarps * L.bytes + k * big + g * L.bytes;
             return c;
         }
     }
@@ -2235,7 +2287,7 @@ static CtaShape plan_cta(const SliceLayout &L, int max_n1, int S, int regs_per_t
 // Shared-memory-only kernels: the occupancy API.
 static int resident_ctas(const CtaShape &c, int regs_per_thread)
 {
-    const int wpb = c.tmem_warps + c.smem_warps;
+    const int wpb = c.tmem_warps + c.smem_warps + c.gmem_warps;
     int ctas = 32;
     ctas = min(ctas, kSmemPerSm / (c.smem_bytes + 1024));
     if (c.tmem_cols > 0) ctas = min(ctas, 512 / c.tmem_cols);
@@ -2248,7 +2300,7 @@ static int resident_ctas(const CtaShape &c, int regs_per_thread)
 template <int S, int MODE>
 int resident_ctas_of(const CtaShape &c)
 {
-    const int wpb = c.tmem_warps + c.smem_warps;
+    const int wpb = c.tmem_warps + c.smem_warps + c.gmem_warps;
     if (cudaFuncSetAttribute(ged_solve_kernel<S, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes) != cudaSuccess) return -1;
     if constexpr (MODE == kModeSmem) {
         int ctas = 0;
@@ -2266,7 +2318,7 @@ int launch_solve_as(SolveParams prm, const CtaShape &c, cudaStream_t stream)
 {
     prm.tmem_warps = c.tmem_warps;
     prm.tmem_cols = c.tmem_cols;
-    const int wpb = c.tmem_warps + c.smem_warps;
+    const int wpb = c.tmem_warps + c.smem_warps + c.gmem_warps;
     cudaError_t e = cudaFuncSetAttribute(ged_solve_kernel<S, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes);
     if (e != cudaSuccess) return fail_cuda(e, "ged_solve_batch");
     // Shared-memory carve-out.  Packed (throughput) launches all ask for the maximum: an SM runs CTAs of one L1/shared split
@@ -2276,13 +2328,17 @@ int launch_solve_as(SolveParams prm, const CtaShape &c, cudaStream_t stream)
     // the 28 KB that the maximum carve-out leaves made a 32-pair AIDS-50+ step 32 % longer.
     // GED_B200_CARVEOUT overrides both (percent; -1 = driver's choice).
     {
-        const int carve = env_int("GED_B200_CARVEOUT", prm.spread ? -1 : 100);
+        // Global-hybrid launches keep only slices in shared memory; alone they run 2.7 % faster with half the carve-out (the L1
+        // then serves their cost-matrix rows), next to the other size classes of a mix 2 % slower -- the uniform split wins
+        // (profiles/r02q_ab_gmem.md).  GED_B200_CARVEOUT_G overrides it for them.
+        const int carve_packed = env_int("GED_B200_CARVEOUT", prm.spread ? -1 : 100);
+        const int carve = MODE == kModeHybridG ? env_int("GED_B200_CARVEOUT_G", carve_packed) : carve_packed;
         e = cudaFuncSetAttribute(ged_solve_kernel<S, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (e != cudaSuccess) return fail_cuda(e, "ged_solve_batch");
     }
     if (env_int("GED_B200_VERBOSE", 0))
-        fprintf(stderr, "[ged_b200] solve<S=%d> count=%d max_n=(%d,%d) cta: %d tmem warps (%d cols) + %d smem warps, %d B dynamic smem\n",
-                S, prm.count, prm.pairs.max_n1, prm.pairs.max_n2, c.tmem_warps, c.tmem_cols, c.smem_warps, c.smem_bytes);
+        fprintf(stderr, "[ged_b200] solve<S=%d> count=%d max_n=(%d,%d) cta: %d tmem warps (%d cols) + %d smem warps + %d gmem warps, %d B dynamic smem\n",
+                S, prm.count, prm.pairs.max_n1, prm.pairs.max_n2, c.tmem_warps, c.tmem_cols, c.smem_warps, c.gmem_warps, c.smem_bytes);
     // Launch shape (ged_solve_desc.launch_hint).  Packed: persistent CTAs (no more than the device holds at once) pulling
     // from the work queue.  Spread (a latency-bound call of a few hundred candidates): one candidate per CTA until every
     // CTA slot is taken, then a second one per CTA, ... -- measured 7-13 % shorter steps at 60-270 candidates of AIDS-50+
@@ -2312,10 +2368,12 @@ int launch_solve_as(SolveParams prm, const CtaShape &c, cudaStream_t stream)
 template <int S>
 int solve_regs()
 {
-    cudaFuncAttributes a, b;
+    cudaFuncAttributes a, b, g;
     if (cudaFuncGetAttributes(&a, ged_solve_kernel<S, kModeTmem>) != cudaSuccess) return -1;
     if (cudaFuncGetAttributes(&b, ged_solve_kernel<S, kModeHybrid>) != cudaSuccess) return -1;
-    return a.numRegs > b.numRegs ? a.numRegs : b.numRegs;
+    if (cudaFuncGetAttributes(&g, ged_solve_kernel<S, kModeHybridG>) != cudaSuccess) return -1;
+    const int r = a.numRegs > b.numRegs ? a.numRegs : b.numRegs;
+    return r > g.numRegs ? r : g.numRegs;
 }
 
 template <int S>
@@ -2333,8 +2391,12 @@ int launch_solve(const SolveParams &prm, cudaStream_t stream)
         if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess)
             prefer_smem = prm.count > sms;
     }
-    const CtaShape c = plan_cta(prm.layout, prm.pairs.max_n1, S, regs, prefer_smem);
+    // global-memory warps need the third matrix of the scratch rows, and rows long enough for the lanes that read past n2
+    const int mn = prm.pairs.max_n1 < prm.pairs.max_n2 ? prm.pairs.max_n1 : prm.pairs.max_n2;
+    const bool allow_gmem = prm.workspace && prm.ws_mats >= 3 && mn >= 31 && !prm.spread;
+    const CtaShape c = plan_cta(prm.layout, prm.pairs.max_n1, S, regs, prefer_smem, allow_gmem);
     if (c.smem_bytes > kMaxSmemBytes) return fail(GED_E_TOO_LARGE, "pair too large for one warp's shared-memory slice");
+    if (c.tmem_warps > 0 && c.gmem_warps > 0) return launch_solve_as<S, kModeHybridG>(prm, c, stream);
     if (c.tmem_warps > 0 && c.smem_warps > 0) return launch_solve_as<S, kModeHybrid>(prm, c, stream);
     return c.tmem_warps > 0 ? launch_solve_as<S, kModeTmem>(prm, c, stream) : launch_solve_as<S, kModeSmem>(prm, c, stream);
 }
@@ -2413,8 +2475,9 @@ int GED_CAT(resident_solve_s, GED_TU_S)(const SliceLayout &L, int max_n1)
 {
     const int regs = solve_regs<GED_TU_S>();
     if (regs < 0) return -1;
-    const CtaShape c = plan_cta(L, max_n1, GED_TU_S, regs);
-    const int wpb = c.tmem_warps + c.smem_warps;
+    const CtaShape c = plan_cta(L, max_n1, GED_TU_S, regs, false, true);       // upper bound: with global-memory warps
+    const int wpb = c.tmem_warps + c.smem_warps + c.gmem_warps;
+    if (c.tmem_warps > 0 && c.gmem_warps > 0) return resident_ctas_of<GED_TU_S, kModeHybridG>(c) * wpb;
     if (c.tmem_warps > 0 && c.smem_warps > 0) return resident_ctas_of<GED_TU_S, kModeHybrid>(c) * wpb;
     return (c.tmem_warps > 0 ? resident_ctas_of<GED_TU_S, kModeTmem>(c) : resident_ctas_of<GED_TU_S, kModeSmem>(c)) * wpb;
 }
@@ -2500,6 +2563,7 @@ int ged_solve_batch(const ged_solve_desc *d, const ged_solve_out *o, void *strea
     prm.ws_locks = d->workspace_locks;
     prm.ws_slots = d->workspace_slots;
     prm.ws_stride = d->workspace_stride ? d->workspace_stride : d->mat_stride;
+    prm.ws_mats = d->workspace_mats >= 3 ? 3 : 2;
     if (prm.ws_slots < 0 || (prm.ws_slots > 0 && !prm.ws_locks)) return fail(GED_E_BADARG, "ged_solve_batch: workspace_slots needs workspace_locks");
     if (prm.ws_stride < need) return fail(GED_E_BADARG, "ged_solve_batch: workspace_stride < (max_n1+1)*(max_n2+1)");
     prm.order = d->order;
@@ -2640,7 +2704,7 @@ int64_t ged_solve_smem_bytes(int32_t max_n1, int32_t max_n2)
 }
 
 int ged_abi_version(void) { return GED_ABI_VERSION; }
-const char *ged_version(void) { return "ged_b200 0.6.0 (sm_100a; ABI 8; canonical order v2; tensor-memory cost store; persistent work-queue launches; CTA-per-candidate team launches)"; }
+const char *ged_version(void) { return "ged_b200 0.7.0 (sm_100a; ABI 9; canonical order v2; tensor-memory cost store; persistent work-queue launches; CTA-per-candidate team launches)"; }
 const char *ged_last_error(void) { return g_err; }
 
 }  // extern "C"

@@ -12,6 +12,13 @@ from . import _lib
 from .graphs import PairSet
 
 SOLVERS = {"ipfp": _lib.GED_SOLVER_IPFP, "hungarian": _lib.GED_SOLVER_HUNGARIAN}
+# Matrices per scratch row (ged_solve_desc.workspace_mats): X, X*A2^T and a third one that lets throughput launches of pairs
+# above 64 nodes run extra warps whose LAP cost matrix lives in global memory (16 instead of 12 solves per SM at 65-85 nodes).
+WORKSPACE_MATS = 3
+
+
+def _workspace_mats() -> int:
+    return 2 if os.environ.get("GED_B200_WORKSPACE_MATS") == "2" else WORKSPACE_MATS       # 2: tests / A-B runs
 
 
 # calls of at most this many candidates in total are latency-bound (a rollout / beam-search step): one candidate per CTA
@@ -139,7 +146,7 @@ def solve_batch(pairs: PairSet, base_idx=None, edit_u=None, edit_v=None, solver:
     # Scratch rows for the solves in flight (the iterate X and X*A2^T): one region per launch, sized by the number of
     # solves the device can hold at once, claimed row by row inside the kernel (ged_solve_desc.workspace_*).
     launches = [(0, B, m1, m2)] if (plan is None or len(plan[1]) <= 1) else list(plan[1])
-    regions, workspace, locks, legacy = [], None, None, False
+    regions, workspace, locks, legacy, mats = [], None, None, False, _workspace_mats()
     if solver == "ipfp" or x_init is not None:
         with torch.cuda.device(dev):
             floats = rows = 0
@@ -148,7 +155,7 @@ def solve_batch(pairs: PairSet, base_idx=None, edit_u=None, edit_v=None, solver:
                 slots = B if legacy else max(1, min(count, int(lib.ged_solve_max_resident(c1, c2))))
                 stride = (c1 + 1) * (c2 + 1)
                 regions.append((floats, rows, slots, stride))
-                floats += 2 * slots * stride
+                floats += mats * slots * stride
                 rows += slots
         workspace = torch.empty(floats, **f32)
         locks = torch.zeros(rows, **i32)
@@ -174,7 +181,7 @@ def solve_batch(pairs: PairSet, base_idx=None, edit_u=None, edit_v=None, solver:
                              p(score_adj1, _lib.c_u8p), p(score_adj1_off, _lib.c_i64p), p(score_idx, _lib.c_i32p),
                              int(score_adj1_ld), int(max_iter), SOLVERS[solver], p(x_init, _lib.c_f32p), ms, p(workspace, _lib.c_f32p),
                              p(locks, _lib.c_i32p), 0, 0, p(None, _lib.c_i32p), 0, p(None, _lib.c_i32p),
-                             launch_hint_for(B) if launch_hint is None else int(launch_hint))
+                             launch_hint_for(B) if launch_hint is None else int(launch_hint), mats)
 
     def set_region(k):
         if counters is not None:

@@ -76,6 +76,33 @@ def test_cost_store_variants_are_bit_identical(cuda_device, config, num, per, mo
     assert np.array_equal(outs[0].rowmatch[1, :g1.n].cpu().numpy(), o["rowmatch"])
 
 
+@pytest.mark.parametrize("config", ["n=80", "n=85"])
+def test_global_memory_warps_are_bit_identical(cuda_device, config, monkeypatch):
+    """A packed launch of 75-85-node pairs runs tensor-memory warps next to warps whose LAP cost matrix is the third matrix of
+    their scratch row (16 instead of 12 solves per SM): same bits as the shared-memory hybrid CTA (switch off), as a caller
+    that hands rows of two matrices only, and as the oracle."""
+    from ppo_bihyb_b200 import _lib
+    pairs = synthetic.make_pairs(config, 3, seed_offset=67)
+    edits = synthetic.make_edits(pairs, 16, seed_offset=67)
+    ps = PairSet.from_host(pairs, cuda_device)
+    n = int(config[2:])
+    sms = torch.cuda.get_device_properties(cuda_device).multi_processor_count
+    assert _lib.load().ged_solve_max_resident(n, n) == 16 * sms         # 2 CTAs of 4 tensor-memory + 4 global-memory warps
+    outs = []
+    for gm, mats in (("1", "3"), ("0", "3"), ("1", "2")):
+        monkeypatch.setenv("GED_B200_GMEM_WARPS", gm)
+        monkeypatch.setenv("GED_B200_WORKSPACE_MATS", mats)
+        outs.append(_solve(ps, edits, launch_hint=0))
+    for o in outs[1:]:
+        assert torch.equal(o.ged, outs[0].ged) and torch.equal(o.rowmatch, outs[0].rowmatch)
+        assert torch.equal(o.colmatch, outs[0].colmatch) and torch.equal(o.iters, outs[0].iters)
+    for b in (5, 40):                                                    # candidates 4..7 of a CTA go to its global-memory warps
+        g1, g2 = pairs[edits[0][b]]
+        o = go.solve(g1.adj, g2.adj, label_node_cost(g1.labels, g2.labels), edit=(int(edits[1][b]), int(edits[2][b])))
+        assert float(outs[0].ged[b]) == o["ged"] and int(outs[0].iters[b]) == o["iters"]
+        assert np.array_equal(outs[0].rowmatch[b, :g1.n].cpu().numpy(), o["rowmatch"])
+
+
 def test_scratch_rows_are_recycled_without_interference(cuda_device):
     """More candidates than the device can hold at once: scratch rows are claimed and released by the solves in flight.
     The result must equal the one-launch-per-candidate-subset result (which uses disjoint rows)."""
