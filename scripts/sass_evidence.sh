@@ -16,8 +16,8 @@ echo
 echo "## scan loop, ged_solve_kernel<2, kModeTmem>"
 python scripts/sass_scan_loop.py ppo-bihyb_b200/build/ged_s2.o "ged_solve_kernelILi2ELi1E" --dump | awk "/^loop 0x1/{exit} {print}"
 echo
-echo "## scan loop instruction mix, other instantiations (first scan loop of each)"
-for s in 1 3 4; do for m in 0 1 2; do
+echo "## scan loop instruction mix, other instantiations (first scan loop of each; mode 0 shared, 1 tensor, 2 tensor + shared, 3 tensor + global memory)"
+for s in 1 3 4; do for m in 0 1 2 3; do
   python scripts/sass_scan_loop.py ppo-bihyb_b200/build/ged_s$s.o "ged_solve_kernelILi${s}ELi${m}E" 2>/dev/null | sed -n 2,3p | sed "s/^/S=$s mode=$m  /"
 done; done
 echo "team W=4:"; python scripts/sass_scan_loop.py ppo-bihyb_b200/build/ged_team.o "ged_solve_team_kernelILi4ELi4E" 2>/dev/null | sed -n 2,3p
