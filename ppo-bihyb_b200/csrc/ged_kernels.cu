@@ -15,7 +15,9 @@
 //   * TmemCost: in TENSOR MEMORY (tcgen05.st / tcgen05.ld, 32x32b shape): TMEM is 128 lanes x 512 columns of 32 bits
 //     per SM, each warp of a CTA owns one 32-lane quarter, element (i, a) sits at lane a & 31, column i * S + (a >> 5);
 //     a row of the matrix is ONE tcgen05.ld.  It is used purely as a second 256 KB scratchpad (no MMA): a hybrid CTA
-//     runs 4 TMEM-backed solves next to k shared-memory-backed ones (one instantiation for both, AnyCost).
+//     runs 4 TMEM-backed solves next to k shared-memory-backed ones (one instantiation for both, AnyCost);
+//   * GmemCost: in the solve's scratch row in global memory (L2 resident), for the four extra warps of a tensor + global
+//     hybrid CTA where tensor and shared memory together hold only 12 matrices per SM (75-85 nodes): 16 solves per SM.
 // The fractional IPFP iterate X and Y = X A2^T live in global memory (touched only between LAPs, L2 resident).
 // K is never built: K vec(X) is evaluated from the two bit-packed adjacency factors.  Warps never synchronise with each
 // other (the only CTA-wide barriers bracket the TMEM allocation).
@@ -1244,7 +1246,7 @@ __device__ void solve_one(const SolveParams &prm, int b, int slot, const Slice &
 // tmem_warps slices without a cost block, then the others with one.
 // MODE = kModeSmem: no tensor-memory instruction in the binary at all (a CTA of a kernel that may allocate tensor memory
 // holds the SM's allocation permit until it relinquishes it, which keeps other CTAs off the SM).
-constexpr int kMaxCtaWarps = 8;          // 4 tensor-memory warps + at most 4 shared-memory warps
+constexpr int kMaxCtaWarps = 8;          // 4 tensor-memory warps + at most 4 shared-memory (or global-memory) warps
 
 // Spread (latency-bound) launches give every CTA ONE candidate in the first round.  Warp w of a CTA runs on SM sub-partition
 // w % 4 (tensor memory ties a warp to the lane quarter of its sub-partition), so if that candidate always went to warp 0,
