@@ -14,7 +14,9 @@ dev = torch.device("cuda:0")
 go.lib()
 threads = os.cpu_count() or 1
 bad_total = 0
-for config, P in (("aids-20-30", 32), ("aids-30-50", 32), ("aids-50+", 48), ("n=70", 8), ("n=85", 8), ("n=100", 6), ("n=130", 3)):
+CONFIGS = (("aids-20-30", 32), ("aids-30-50", 32), ("aids-50+", 48), ("n=70", 8), ("n=80", 8), ("n=85", 8), ("n=100", 6), ("n=130", 3))
+only = os.environ.get("SOAK_CONFIGS")        # e.g. SOAK_CONFIGS=aids-50+,n=80,n=85
+for config, P in (c for c in CONFIGS if only is None or c[0] in only.split(",")):
     pairs = synthetic.make_pairs(config, P, seed_offset=4242)
     E = max(1, per // P)
     edits = synthetic.make_edits(pairs, E, seed_offset=4242)
