@@ -113,9 +113,10 @@ typedef struct ged_solve_desc {
      * Results are bit-identical under every hint. */
     int32_t launch_hint;
     /* Matrices per workspace row: 0 / 2 = the row holds X and X*A2^T (2 * workspace_stride floats), 3 = it holds a third
-     * matrix of workspace_stride floats (ABI 9).  With the third matrix a throughput launch of pairs above 64 nodes -- where
+     * matrix of workspace_stride floats (ABI 9).  With the third matrix a throughput launch of 75-85-node pairs -- where
      * tensor memory and shared memory together hold the LAP cost matrices of only 12 solves per SM -- runs additional warps
-     * whose cost matrix lives there (L2 resident): 16 solves per SM, +12 % at 80 nodes.  Results are bit-identical. */
+     * whose cost matrix lives there (L2 resident): 16 solves per SM, +10 % at 80 nodes.  Results are bit-identical; a caller
+     * that passes 0 / 2 gets the tensor + shared-memory plan. */
     int32_t workspace_mats;
 } ged_solve_desc;
 
