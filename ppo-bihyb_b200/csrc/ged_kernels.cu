@@ -1023,6 +1023,7 @@ struct SolveParams {
     int spread;              // static assignment: 1 = candidate blockIdx + warp * gridDim (spread over CTAs), 0 = CTA-major
     int tmem_warps;          // 0 or 4: warps 0..3 of every CTA keep their cost matrix in tensor memory
     int tmem_cols;           // columns allocated per CTA (power of two >= 32)
+    int two_ended;           // tensor + global hybrid launches: the work queue is taken from both ends (see ged_solve_kernel)
     int ws_mats;             // matrices per scratch row: 2 (X, X A2^T) or 3 (+ a cost matrix for a global-memory warp)
     ged_solve_out out;
     SliceLayout layout;
@@ -1313,7 +1314,18 @@ __global__ void __launch_bounds__(GED_LB_THREADS(S, MODE), GED_LB_CTAS(S, MODE))
 #endif
     for (int slot = prm.spread ? blockIdx.x + vwarp * gridDim.x : gwarp;;) {      // static assignment (see launch_solve_as)
         if (prm.work_counter) {
-            if ((threadIdx.x & 31) == 0) slot = atomicAdd(prm.work_counter, 1);
+            if (MODE == kModeHybridG && prm.two_ended) {
+                // Two-ended queue: the tensor-memory warps take the list from its front (heaviest candidates), the slower
+                // global-memory warps from its back (lightest).  One int32 holds both cursors (front in the low half, back
+                // in the high half): an atomic add returns a unique (front, back) state, the taker's index is its own
+                // half, and it is valid while front + back < count -- of two takers that would meet at the same index,
+                // the later one sees the earlier one's increment and finds the list exhausted.
+                if ((threadIdx.x & 31) == 0) {
+                    const unsigned old = (unsigned)atomicAdd(prm.work_counter, tm ? 1 : (1 << 16));
+                    const int f = (int)(old & 0xffffu), bk = (int)(old >> 16);
+                    slot = (f + bk < prm.count) ? (tm ? f : prm.count - 1 - bk) : prm.count;
+                }
+            } else if ((threadIdx.x & 31) == 0) slot = atomicAdd(prm.work_counter, 1);
             slot = __shfl_sync(kFull, slot, 0);
         }
         if (slot >= prm.count) break;
@@ -2358,6 +2370,9 @@ int launch_solve_as(SolveParams prm, const CtaShape &c, cudaStream_t stream)
         } else {
             prm.spread = 0;
             if (prm.work_counter && grid > resident) grid = resident;
+            // both cursors of the two-ended queue share the caller's one int32 (16 bits each; every warp adds once more
+            // than it takes)
+            prm.two_ended = MODE == kModeHybridG && prm.work_counter && prm.count + grid * wpb < 60000 && env_int("GED_B200_TWO_ENDED", 1);
         }
     }
     ged_solve_kernel<S, MODE><<<grid, wpb * 32, c.smem_bytes, stream>>>(prm);
@@ -2566,6 +2581,7 @@ int ged_solve_batch(const ged_solve_desc *d, const ged_solve_out *o, void *strea
     prm.ws_slots = d->workspace_slots;
     prm.ws_stride = d->workspace_stride ? d->workspace_stride : d->mat_stride;
     prm.ws_mats = d->workspace_mats >= 3 ? 3 : 2;
+    prm.two_ended = 0;
     if (prm.ws_slots < 0 || (prm.ws_slots > 0 && !prm.ws_locks)) return fail(GED_E_BADARG, "ged_solve_batch: workspace_slots needs workspace_locks");
     if (prm.ws_stride < need) return fail(GED_E_BADARG, "ged_solve_batch: workspace_stride < (max_n1+1)*(max_n2+1)");
     prm.order = d->order;
