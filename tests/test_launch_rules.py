@@ -44,3 +44,32 @@ def test_bench_workload_partitions():
         for _, b, _, _ in shards:
             assert set(np.unique(b)) == set(range(args.pairs))
         assert ("in total" if scaling == "strong" else "per GPU") in bench.workload_name(args, world)
+
+
+def test_two_ended_queue_protocol_takes_every_candidate_once():
+    """Model of the two-ended work queue of the tensor + global hybrid launches (csrc/ged_kernels.cu, ged_solve_kernel): one
+    int32 holds both cursors (front: low 16 bits, back: high 16 bits); a taker adds 1 or 1 << 16, reads the OLD value, and takes
+    index front (fast warps) or count - 1 - back (slow warps) while front + back < count.  Whatever the interleaving of fast and
+    slow takers, every candidate is taken exactly once, and every warp's final (failing) attempt leaves the halves intact."""
+    rng = np.random.default_rng(7)
+    for count in (1, 2, 7, 270, 5120):
+        for p_fast in (0.0, 0.3, 0.5, 0.9, 1.0):
+            counter, taken, attempts = 0, [], 0
+            warps = 2368
+            done = np.zeros(warps, bool)
+            fast = np.arange(warps) % 8 < 4                      # warps 0..3 of a CTA are the tensor-memory ones
+            while not done.all():
+                w = int(rng.choice(np.nonzero(~done)[0]))
+                if p_fast in (0.0, 1.0) and fast[w] != (p_fast == 1.0) and (~done & (fast == (p_fast == 1.0))).any():
+                    continue                                     # one kind of warp runs alone until it is exhausted
+                old = counter
+                counter += 1 if fast[w] else 1 << 16
+                attempts += 1
+                f, b = old & 0xffff, old >> 16
+                if f + b < count:
+                    taken.append(f if fast[w] else count - 1 - b)
+                else:
+                    done[w] = True
+            assert sorted(taken) == list(range(count)), (count, p_fast)
+            assert attempts == count + warps and (counter & 0xffff) + (counter >> 16) == attempts
+            assert (counter & 0xffff) < 1 << 16 and (counter >> 16) < 1 << 16      # no carry between the halves (count + warps < 60000)
